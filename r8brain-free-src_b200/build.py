@@ -1,0 +1,65 @@
+"""In-tree build of libr8bgpu.so (the C-ABI library) for sm_100a.
+
+nvcc cross-compiles without a GPU.  The library is written next to this file so it travels
+with the gpurun snapshot; it is git-ignored.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libr8bgpu.so")
+SOURCES = ["r8b_capi.cu", "r8b_kernels.cu", "r8b_plan.cpp", "r8b_design.cpp"]
+HEADERS = ["r8b_fft.cuh", "r8b_kernels.h", "r8b_plan.h", "r8b_design.h", "r8b_tables.inc",
+           os.path.join("..", "..", "include", "r8bgpu.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17", "--shared",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-fno-fast-math",
+    "-Xptxas", "-v",
+]
+
+
+def find_nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile the library if it is missing or stale.  Returns the path of the .so."""
+    if not force and not needs_build():
+        return LIB
+    nvcc = find_nvcc()
+    if nvcc is None:
+        if os.path.exists(LIB):
+            return LIB  # GPU box without a toolchain: use the prebuilt library
+        raise RuntimeError("nvcc not found and no prebuilt libr8bgpu.so present")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log = os.path.join(HERE, "build.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("nvcc failed (see %s)" % log)
+    os.replace(LIB + ".tmp", LIB)
+    if verbose:
+        sys.stdout.write(r.stdout)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,611 @@
+// r8b_capi.cu -- the engine behind include/r8bgpu.h: device-resident per-channel state, the
+// per-call launch sequence, and the extern "C" boundary.
+//
+// Per-channel state in HBM, all planar [channel][...]:
+//   * input history ring      : the most recent source samples the first stage may re-read
+//   * one ring per stage link : the stream between stage i and i+1, absolute-indexed,
+//                               capacity = pow2 >= (max samples per call + look-back of stage i+1)
+// Shared read-only per plan: filter spectrum (slot order, pre-scaled), FFT twiddles, fractional
+// delay bank.  All integer scheduling state lives on the host (Schedule), once per batch.
+#include "../../include/r8bgpu.h"
+
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "r8b_fft.cuh"
+#include "r8b_kernels.h"
+#include "r8b_plan.h"
+
+using namespace r8bgpu;
+
+namespace {
+
+thread_local std::string g_err;
+
+void set_err(const std::string& s) { g_err = s; }
+
+bool cuda_ok(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return true;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+long long next_pow2(long long v)
+{
+    long long p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            ok = false;
+            return;
+        }
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// Spectrum of the polyphase-packed filter in FFT slot order (see k_blockconv).
+template <int M>
+void fill_slot_order(const std::vector<double2>& nat, std::vector<double2>& out)
+{
+    out.resize((size_t) M);
+    for (int k = 0; k < M; k++) out[(size_t) slot_of<M>(k)] = nat[(size_t) k];
+}
+
+void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec_slots,
+                    std::vector<double2>& tw)
+{
+    const int M = 1 << fft_log2;
+    const int L = s.lp.half_len, U = s.up;
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    std::vector<long double> cs((size_t) M), sn((size_t) M);
+    for (int k = 0; k < M; k++) {
+        // exact octant symmetries are not needed at long-double accuracy
+        const long double a = two_pi * (long double) k / (long double) M;
+        cs[(size_t) k] = cosl(a);
+        sn[(size_t) k] = sinl(a);
+    }
+    tw.resize((size_t) M);
+    for (int k = 0; k < M; k++) tw[(size_t) k] = make_double2((double) cs[(size_t) k], (double) -sn[(size_t) k]);
+
+    // g[j] = h[U*j] + i*h[U*j+1] (U==2) or h[j] (U==1), j in [-lg, lg]
+    const int lg = (L + U - 1) / U;
+    const double* h = s.lp.taps.data() + L; // h[-L..L]
+    auto tap = [&](long long idx) -> long double {
+        return (idx < -L || idx > L) ? 0.0L : (long double) h[idx];
+    };
+    const long double scale = 1.0L / ((long double) M * (U == 2 ? 2.0L : 1.0L));
+    std::vector<double2> nat((size_t) M);
+    for (int k = 0; k < M; k++) {
+        long double re = 0.0L, im = 0.0L;
+        for (int j = -lg; j <= lg; j++) {
+            const long double gr = tap((long long) U * j);
+            const long double gi = (U == 2) ? tap((long long) U * j + 1) : 0.0L;
+            if (gr == 0.0L && gi == 0.0L) continue;
+            const int idx = (int) ((((long long) j * k) % M + M) % M);
+            const long double c = cs[(size_t) idx], sv = -sn[(size_t) idx]; // exp(-i*2pi*j*k/M)
+            re += gr * c - gi * sv;
+            im += gr * sv + gi * c;
+        }
+        nat[(size_t) k] = make_double2((double) (re * scale), (double) (im * scale));
+    }
+    switch (fft_log2) {
+    case 10: fill_slot_order<1024>(nat, spec_slots); break;
+    case 11: fill_slot_order<2048>(nat, spec_slots); break;
+    default: fill_slot_order<4096>(nat, spec_slots); break;
+    }
+}
+
+int choose_fft_log2(int lg)
+{
+    if (const char* e = getenv("R8BGPU_FFT_LOG2")) {
+        const int v = atoi(e);
+        if (v >= 10 && v <= 12 && (1 << v) - 2 * lg >= 64) return v;
+    }
+    int best = -1;
+    double best_cost = 0.0;
+    for (int b = 10; b <= 12; b++) {
+        const int m = 1 << b;
+        const int valid = m - 2 * lg;
+        if (valid < 64) continue;
+        const double cost = (double) b * m / valid;
+        if (best < 0 || cost < best_cost) {
+            best = b;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
+
+struct StageDev {
+    // BLOCKCONV
+    int fft_log2 = 0, lg = 0;
+    double2* spec = nullptr;
+    double2* tw = nullptr;
+    // FRAC
+    double* bank = nullptr;
+    // source ring of this stage (for stage 0: the input history ring)
+    double* ring = nullptr;
+    long long ring_cap = 0;
+};
+
+} // namespace
+
+struct r8bgpu_plan {
+    Plan p;
+};
+
+struct r8bgpu_batch {
+    const Plan* plan = nullptr;
+    Plan plan_copy; // batches own a copy so the plan handle may be destroyed first
+    int n_ch = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Schedule sched;
+    std::vector<StageDev> dev;
+    std::vector<StageCall> calls;
+    unsigned long long launches = 0;
+    unsigned long long dev_bytes = 0;
+    // staging for the host-pointer entry point
+    double* st_in = nullptr;
+    double* st_out = nullptr;
+
+    ~r8bgpu_batch()
+    {
+        DeviceGuard g(device);
+        for (auto& d : dev) {
+            cudaFree(d.spec);
+            cudaFree(d.tw);
+            cudaFree(d.bank);
+            cudaFree(d.ring);
+        }
+        cudaFree(st_in);
+        cudaFree(st_out);
+    }
+};
+
+extern "C" {
+
+const char* r8bgpu_last_error(void) { return g_err.c_str(); }
+const char* r8bgpu_version(void) { return "r8bgpu 0.1 (sm_100a)"; }
+
+r8bgpu_plan* r8bgpu_plan_create(double src, double dst, int max_in_len, double tb, double atten, int phase,
+                                int extfft, int fasttiming)
+{
+    std::unique_ptr<r8bgpu_plan> h(new r8bgpu_plan);
+    if (!h->p.build(src, dst, max_in_len, tb, atten, phase, extfft, fasttiming)) {
+        set_err("plan_create: " + h->p.error);
+        return nullptr;
+    }
+    return h.release();
+}
+
+r8bgpu_plan* r8bgpu_plan_create_stage(int kind, const double* params, int n_params, int max_in_len, int extfft)
+{
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n_params && i < 8; i++) a[i] = params[i];
+    std::unique_ptr<r8bgpu_plan> h(new r8bgpu_plan);
+    if (max_in_len <= 0 || !h->p.build_single(kind, a, max_in_len, extfft)) {
+        set_err("plan_create_stage: " + h->p.error);
+        return nullptr;
+    }
+    return h.release();
+}
+
+void r8bgpu_plan_destroy(r8bgpu_plan* plan) { delete plan; }
+int r8bgpu_plan_max_out_len(const r8bgpu_plan* plan) { return plan->p.max_out_len; }
+int r8bgpu_plan_in_len_before_out_pos(const r8bgpu_plan* plan, int pos) { return plan->p.in_len_before_out_pos(pos); }
+int r8bgpu_plan_input_required_for_output(const r8bgpu_plan* plan, int n) { return plan->p.input_required_for_output(n); }
+double r8bgpu_plan_latency_frac(const r8bgpu_plan*) { return 0.0; } // linear-phase chains leave no fractional latency
+int r8bgpu_plan_is_passthrough(const r8bgpu_plan* plan) { return plan->p.passthrough ? 1 : 0; }
+int r8bgpu_plan_stage_count(const r8bgpu_plan* plan) { return (int) plan->p.stages.size(); }
+
+static int stage_data_len(const StageDesc& s)
+{
+    switch (s.kind) {
+    case ST_BLOCKCONV: return s.lp.kernel_len;
+    case ST_FRAC_WHOLE:
+    case ST_FRAC_POLY: return (int) s.bank.table.size();
+    default: return s.hb_taps;
+    }
+}
+
+int r8bgpu_plan_stage_info(const r8bgpu_plan* plan, int stage, r8bgpu_stage_info* info)
+{
+    if (stage < 0 || stage >= (int) plan->p.stages.size() || info == nullptr) {
+        set_err("stage_info: bad stage index");
+        return -1;
+    }
+    const StageDesc& s = plan->p.stages[(size_t) stage];
+    memset(info, 0, sizeof *info);
+    info->kind = (int) s.kind;
+    info->up = s.up;
+    info->down = s.down;
+    info->max_out_len = s.max_out_len;
+    info->data_len = stage_data_len(s);
+    switch (s.kind) {
+    case ST_BLOCKCONV:
+        info->kernel_len = s.lp.kernel_len;
+        info->latency = s.latency;
+        info->ref_input_len = s.ref_input_len;
+        info->block_len_bits = s.lp.block_len_bits;
+        break;
+    case ST_FRAC_WHOLE:
+    case ST_FRAC_POLY:
+        info->kernel_len = s.bank.filter_len;
+        info->fracs = s.bank.fracs;
+        info->in_step = s.in_step;
+        info->out_step = s.out_step;
+        info->order = s.bank.order;
+        info->atten = s.bank.atten;
+        break;
+    default:
+        info->kernel_len = s.hb_taps;
+        info->atten = s.hb_atten;
+        break;
+    }
+    return 0;
+}
+
+int r8bgpu_plan_stage_data(const r8bgpu_plan* plan, int stage, double* out, int cap)
+{
+    if (stage < 0 || stage >= (int) plan->p.stages.size()) {
+        set_err("stage_data: bad stage index");
+        return -1;
+    }
+    const StageDesc& s = plan->p.stages[(size_t) stage];
+    const double* src = s.kind == ST_BLOCKCONV ? s.lp.taps.data()
+        : (s.kind == ST_FRAC_WHOLE || s.kind == ST_FRAC_POLY) ? s.bank.table.data() : s.hb.data();
+    const int n = stage_data_len(s);
+    const int c = n < cap ? n : cap;
+    if (out != nullptr && c > 0) memcpy(out, src, (size_t) c * sizeof(double));
+    return n;
+}
+
+int r8bgpu_plan_describe(const r8bgpu_plan* plan, char* buf, int cap)
+{
+    const std::string d = plan->p.describe();
+    if (buf != nullptr && cap > 0) {
+        const size_t n = d.size() < (size_t) cap - 1 ? d.size() : (size_t) cap - 1;
+        memcpy(buf, d.data(), n);
+        buf[n] = 0;
+    }
+    return (int) d.size();
+}
+
+int r8bgpu_plan_simulate(const r8bgpu_plan* plan, const int* lens, int n_calls, int* counts)
+{
+    Schedule sc;
+    sc.init(&plan->p);
+    std::vector<StageCall> calls;
+    for (int i = 0; i < n_calls; i++) {
+        if (lens[i] < 0 || lens[i] > plan->p.max_in_len) {
+            set_err("simulate: block length outside [0, MaxInLen]");
+            return -1;
+        }
+        counts[i] = sc.advance(lens[i], calls);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+
+int r8bgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int device)
+{
+    if (plan == nullptr || n_channels <= 0 || n_channels > 65535) {
+        set_err("batch_create: need a plan and 1..65535 channels");
+        return nullptr;
+    }
+    int ndev = 0;
+    if (!cuda_ok(cudaGetDeviceCount(&ndev), "batch_create: cudaGetDeviceCount") || ndev == 0) {
+        if (g_err.empty()) set_err("batch_create: no CUDA device (this engine has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 && !cuda_ok(cudaGetDevice(&device), "batch_create: cudaGetDevice")) return nullptr;
+    if (device >= ndev) {
+        set_err("batch_create: device index out of range");
+        return nullptr;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) {
+        set_err("batch_create: cudaSetDevice failed");
+        return nullptr;
+    }
+    std::unique_ptr<r8bgpu_batch> b(new r8bgpu_batch);
+    b->plan_copy = plan->p;
+    b->plan = &b->plan_copy;
+    b->n_ch = n_channels;
+    b->device = device;
+    b->sched.init(b->plan);
+    const auto& st = b->plan->stages;
+    b->dev.resize(st.size());
+    for (size_t i = 0; i < st.size(); i++) {
+        const StageDesc& s = st[i];
+        StageDev& d = b->dev[i];
+        const long long emit_in = (i == 0) ? 0 : st[i - 1].max_out_len;
+        d.ring_cap = next_pow2((long long) s.src_history + emit_in + 64);
+        const size_t ring_bytes = (size_t) d.ring_cap * (size_t) n_channels * sizeof(double);
+        if (!cuda_ok(cudaMalloc(&d.ring, ring_bytes), "batch_create: cudaMalloc(ring)")) return nullptr;
+        b->dev_bytes += ring_bytes;
+        if (s.kind == ST_BLOCKCONV) {
+            if (s.up > 2) {
+                set_err("batch_create: BlockConvolver up-factor 3 is not implemented yet");
+                return nullptr;
+            }
+            d.lg = (s.lp.half_len + s.up - 1) / s.up;
+            d.fft_log2 = choose_fft_log2(d.lg);
+            if (d.fft_log2 < 0) {
+                set_err("batch_create: low-pass kernel too long for the in-shared-memory FFT tiles");
+                return nullptr;
+            }
+            std::vector<double2> spec, tw;
+            build_spectrum(s, d.fft_log2, spec, tw);
+            const size_t nb = spec.size() * sizeof(double2);
+            if (!cuda_ok(cudaMalloc(&d.spec, nb), "cudaMalloc(spec)")) return nullptr;
+            if (!cuda_ok(cudaMalloc(&d.tw, nb), "cudaMalloc(tw)")) return nullptr;
+            if (!cuda_ok(cudaMemcpy(d.spec, spec.data(), nb, cudaMemcpyHostToDevice), "copy spec")) return nullptr;
+            if (!cuda_ok(cudaMemcpy(d.tw, tw.data(), nb, cudaMemcpyHostToDevice), "copy tw")) return nullptr;
+            b->dev_bytes += 2 * nb;
+        } else if (s.kind == ST_FRAC_WHOLE || s.kind == ST_FRAC_POLY) {
+            const size_t nb = s.bank.table.size() * sizeof(double);
+            if (!cuda_ok(cudaMalloc(&d.bank, nb), "cudaMalloc(bank)")) return nullptr;
+            if (!cuda_ok(cudaMemcpy(d.bank, s.bank.table.data(), nb, cudaMemcpyHostToDevice), "copy bank")) return nullptr;
+            b->dev_bytes += nb;
+        }
+    }
+    r8bgpu_batch* raw = b.release();
+    if (r8bgpu_batch_clear(raw) != 0) {
+        delete raw;
+        return nullptr;
+    }
+    return raw;
+}
+
+void r8bgpu_batch_destroy(r8bgpu_batch* batch) { delete batch; }
+int r8bgpu_batch_channels(const r8bgpu_batch* b) { return b->n_ch; }
+unsigned long long r8bgpu_batch_kernel_launches(const r8bgpu_batch* b) { return b->launches; }
+unsigned long long r8bgpu_batch_device_bytes(const r8bgpu_batch* b) { return b->dev_bytes; }
+
+int r8bgpu_batch_set_stream(r8bgpu_batch* b, void* stream)
+{
+    b->stream = (cudaStream_t) stream;
+    return 0;
+}
+
+int r8bgpu_batch_clear(r8bgpu_batch* b)
+{
+    DeviceGuard g(b->device);
+    b->sched.clear();
+    for (auto& d : b->dev) {
+        if (!cuda_ok(cudaMemsetAsync(d.ring, 0, (size_t) d.ring_cap * (size_t) b->n_ch * sizeof(double), b->stream),
+                     "batch_clear: cudaMemsetAsync"))
+            return -1;
+    }
+    return 0;
+}
+
+int r8bgpu_batch_sync(r8bgpu_batch* b)
+{
+    DeviceGuard g(b->device);
+    return cuda_ok(cudaStreamSynchronize(b->stream), "batch_sync") ? 0 : -1;
+}
+
+int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, int l, double* d_out,
+                         size_t out_stride, int out_cap)
+{
+    if (b == nullptr || l < 0 || l > b->plan->max_in_len) {
+        set_err("batch_process: l must be in [0, MaxInLen]");
+        return -1;
+    }
+    if (l > 0 && d_in == nullptr) {
+        set_err("batch_process: null input");
+        return -1;
+    }
+    DeviceGuard g(b->device);
+    const Plan& P = *b->plan;
+    const cudaStream_t st = b->stream;
+    if (P.passthrough) { // SrcSampleRate == DstSampleRate: the reference hands the input back
+        if (l > out_cap) {
+            set_err("batch_process: output capacity too small");
+            return -1;
+        }
+        if (l > 0 && !cuda_ok(cudaMemcpy2DAsync(d_out, out_stride * sizeof(double), d_in,
+                                                in_stride * sizeof(double), (size_t) l * sizeof(double),
+                                                (size_t) b->n_ch, cudaMemcpyDeviceToDevice, st),
+                              "batch_process: passthrough copy"))
+            return -1;
+        return l;
+    }
+
+    Schedule saved = b->sched;
+    const int n_out = b->sched.advance(l, b->calls);
+    if (n_out > out_cap || (n_out > 0 && d_out == nullptr)) {
+        b->sched = saved;
+        set_err("batch_process: output capacity too small for this call");
+        return -1;
+    }
+
+    const size_t ns = P.stages.size();
+    for (size_t i = 0; i < ns; i++) {
+        const StageDesc& s = P.stages[i];
+        const StageCall& c = b->calls[i];
+        const StageDev& d = b->dev[i];
+        if (c.e1 <= c.e0) continue;
+        SrcView src;
+        src.ring = d.ring;
+        src.ring_stride = d.ring_cap;
+        src.ring_mask = d.ring_cap - 1;
+        if (i == 0) {
+            src.cur = d_in;
+            src.cur_stride = (long long) in_stride;
+            src.cur_base = c.n0;
+        } else {
+            src.cur = nullptr;
+            src.cur_stride = 0;
+            src.cur_base = LLONG_MAX;
+        }
+        src.avail = c.n1;
+        DstView dst;
+        if (i + 1 == ns) {
+            dst.ptr = d_out;
+            dst.stride = (long long) out_stride;
+            dst.mask = -1;
+            dst.base = c.e0;
+        } else {
+            dst.ptr = b->dev[i + 1].ring;
+            dst.stride = b->dev[i + 1].ring_cap;
+            dst.mask = b->dev[i + 1].ring_cap - 1;
+            dst.base = 0;
+        }
+        switch (s.kind) {
+        case ST_BLOCKCONV: {
+            BlockConvParams p;
+            p.up = s.up;
+            p.down = s.down;
+            p.lg = d.lg;
+            p.fft_log2 = d.fft_log2;
+            p.e0 = c.e0;
+            p.e1 = c.e1;
+            p.m0 = (c.e0 * s.down) / s.up;               // floor; indices are >= 0
+            p.m1 = ((c.e1 - 1) * s.down) / s.up + 1;
+            const int adv_max = (1 << d.fft_log2) - 2 * d.lg;
+            const long long span = p.m1 - p.m0;
+            long long nt = (span + adv_max - 1) / adv_max;
+            if (nt > 1 && (nt & 1)) nt++; // tiles are transformed in pairs
+            p.n_tiles = (int) nt;
+            p.adv = (int) ((span + nt - 1) / nt);
+            p.spec = d.spec;
+            p.tw = d.tw;
+            launch_blockconv(p, src, dst, b->n_ch, st);
+            b->launches++;
+            break;
+        }
+        case ST_FRAC_WHOLE:
+        case ST_FRAC_POLY: {
+            FracParams p;
+            memset(&p, 0, sizeof p);
+            p.flen = s.bank.filter_len;
+            p.fll = s.bank.filter_len / 2 - 1;
+            p.e0 = c.e0;
+            p.e1 = c.e1;
+            p.bank = d.bank;
+            p.in_step = s.in_step;
+            p.out_step = s.out_step;
+            p.fracs = s.bank.fracs;
+            p.ssr = s.src_rate;
+            p.dsr = s.dst_rate;
+            p.in_counter0 = c.in_counter0;
+            p.in_pos_int0 = c.in_pos_int0;
+            p.in_pos_shift = c.in_pos_shift;
+            p.fpos0 = c.fpos0;
+            p.p0 = c.p0;
+            if (s.kind == ST_FRAC_WHOLE) launch_frac_whole(p, src, dst, b->n_ch, st);
+            else launch_frac_poly(p, src, dst, b->n_ch, st);
+            b->launches++;
+            break;
+        }
+        case ST_HBUP:
+        case ST_HBDOWN: {
+            HbParams p;
+            memset(&p, 0, sizeof p);
+            p.ntaps = s.hb_taps;
+            p.e0 = c.e0;
+            p.e1 = c.e1;
+            for (int k = 0; k < s.hb_taps; k++) p.taps[k] = s.hb[(size_t) k];
+            if (s.kind == ST_HBUP) launch_hbup(p, src, dst, b->n_ch, st);
+            else launch_hbdown(p, src, dst, b->n_ch, st);
+            b->launches++;
+            break;
+        }
+        }
+    }
+    // Keep the most recent input samples for the next calls.
+    if (l > 0) {
+        const StageCall& c0 = b->calls[0];
+        const StageDev& d0 = b->dev[0];
+        long long from = c0.n1 - d0.ring_cap;
+        if (from < c0.n0) from = c0.n0;
+        launch_save_tail(d_in, (long long) in_stride, c0.n0, from, c0.n1, d0.ring, d0.ring_cap,
+                         d0.ring_cap - 1, b->n_ch, st);
+        b->launches++;
+    }
+    if (!cuda_ok(cudaGetLastError(), "batch_process: kernel launch")) return -1;
+    return n_out;
+}
+
+int r8bgpu_batch_process_host(r8bgpu_batch* b, const double* h_in, size_t in_stride, int l, double* h_out,
+                              size_t out_stride, int out_cap)
+{
+    if (b == nullptr || l < 0 || l > b->plan->max_in_len) {
+        set_err("batch_process_host: l must be in [0, MaxInLen]");
+        return -1;
+    }
+    DeviceGuard g(b->device);
+    const size_t in_cap = (size_t) b->plan->max_in_len;
+    const size_t o_cap = (size_t) b->plan->max_out_len;
+    if (b->st_in == nullptr) {
+        if (!cuda_ok(cudaMalloc(&b->st_in, in_cap * b->n_ch * sizeof(double)), "process_host: cudaMalloc(in)")) return -1;
+        if (!cuda_ok(cudaMalloc(&b->st_out, o_cap * b->n_ch * sizeof(double)), "process_host: cudaMalloc(out)")) return -1;
+        b->dev_bytes += (in_cap + o_cap) * b->n_ch * sizeof(double);
+    }
+    if (l > 0 && !cuda_ok(cudaMemcpy2DAsync(b->st_in, in_cap * sizeof(double), h_in, in_stride * sizeof(double),
+                                            (size_t) l * sizeof(double), (size_t) b->n_ch,
+                                            cudaMemcpyHostToDevice, b->stream),
+                          "process_host: H2D"))
+        return -1;
+    const int n = r8bgpu_batch_process(b, b->st_in, in_cap, l, b->st_out, o_cap, (int) o_cap);
+    if (n < 0) return n;
+    if (n > out_cap) {
+        set_err("process_host: output capacity too small");
+        return -1;
+    }
+    if (n > 0 && !cuda_ok(cudaMemcpy2DAsync(h_out, out_stride * sizeof(double), b->st_out, o_cap * sizeof(double),
+                                            (size_t) n * sizeof(double), (size_t) b->n_ch,
+                                            cudaMemcpyDeviceToHost, b->stream),
+                          "process_host: D2H"))
+        return -1;
+    if (!cuda_ok(cudaStreamSynchronize(b->stream), "process_host: sync")) return -1;
+    return n;
+}
+
+void* r8bgpu_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (!cuda_ok(cudaMallocHost(&p, bytes), "host_alloc")) return nullptr;
+    return p;
+}
+
+void r8bgpu_host_free(void* p)
+{
+    if (p != nullptr) cudaFreeHost(p);
+}
+
+} // extern "C"

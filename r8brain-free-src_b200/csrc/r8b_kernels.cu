@@ -1,0 +1,309 @@
+// r8b_kernels.cu -- hand-written sm_100a kernels for the CDSPResampler::process() hot path.
+//
+// Every kernel processes ALL channels of a batch in one launch (channel = outer grid
+// dimension); streams are addressed by absolute sample index (see r8b_plan.h), so a kernel
+// is a pure function of (history ring, current input block) -> (output range).
+//
+//   k_blockconv   CDSPBlockConvolver::process + CDSPRealFFT fwd/inv + multiplyBlocksZP +
+//                 mirrorInputSpectrum  (CDSPBlockConvolver.h:252-354,606-629; CDSPRealFFT.h:98-385)
+//   k_frac_whole  CDSPFracInterpolator::convolve0<N>      (CDSPFracInterpolator.h:991-1060)
+//   k_frac_poly   CDSPFracInterpolator::convolve2          (CDSPFracInterpolator.h:1069-1179)
+//   k_hbup        CDSPHBUpsampler::process / convolveN     (CDSPHBUpsampler.h:674-732, .inc)
+//   k_hbdown      CDSPHBDownsampler::process / convolveN   (CDSPHBDownsampler.h:137-239, .inc)
+//
+// fp64 throughout; no tensor cores (1-D convolution, not a dense contraction).
+#include "r8b_kernels.h"
+
+#include <climits>
+
+#include "r8b_fft.cuh"
+
+namespace r8bgpu {
+
+__device__ __forceinline__ double src_read(const SrcView& v, int ch, long long n)
+{
+    if (n >= v.avail) return 0.0;
+    if (n >= v.cur_base) return __ldg(v.cur + (long long) ch * v.cur_stride + (n - v.cur_base));
+    return __ldg(v.ring + (long long) ch * v.ring_stride + (n & v.ring_mask));
+}
+
+__device__ __forceinline__ void dst_write(const DstView& v, int ch, long long idx, double x)
+{
+    v.ptr[(long long) ch * v.stride + ((idx - v.base) & v.mask)] = x;
+}
+
+// ------------------------------------------------------------------------------------------
+// Overlap-save FIR with built-in xU / :D.
+//
+// Polyphase view of "zero-stuff by U, filter with h, keep every D-th":
+//     y[U*m + r] = sum_j g_r[j] * x[m - j],   g_r[j] = h[U*j + r]
+// One CTA transforms TWO consecutive tiles (a,b) of one channel packed as z = x_a + i*x_b with a
+// single M-point complex FFT.
+//   U == 1: g real  =>  IFFT(Z .* G) = y_a + i*y_b                      (1 inverse for 2 tiles)
+//   U == 2: G = FFT(g_0 + i*g_1); X_a = (Z[k] + conj Z[M-k])/2, X_b = (Z[k] - conj Z[M-k])/(2i);
+//           IFFT(X_t .* G)[m] = y_t[2m] + i*y_t[2m+1]  -- i.e. the inverse transform's interleaved
+//           re/im IS the 2x-rate output stream (this replaces mirrorInputSpectrum + the
+//           double-length inverse real FFT of the reference).
+// Tile geometry: window of M inputs starting at (first valid m) - lg; outputs are valid for
+// local positions [lg, M - lg).
+template <int M, int UP, int NT>
+__global__ void __launch_bounds__(NT) k_blockconv(BlockConvParams p, SrcView src, DstView dst)
+{
+    extern __shared__ double2 smem[];
+    constexpr int PL = fft_padded_len(M);
+    double2* zbuf = smem;
+    double2* wbuf = (UP == 2) ? smem + PL : smem;
+
+    const int tid = threadIdx.x;
+    const int n_pairs = (p.n_tiles + 1) >> 1;
+    const int ch = blockIdx.x / n_pairs;
+    const int pair = blockIdx.x - ch * n_pairs;
+    const int ta = 2 * pair;
+    const bool has_b = (ta + 1) < p.n_tiles;
+    const long long ma = p.m0 + (long long) ta * p.adv; // first valid input-rate position of tile a
+    const long long mb = ma + p.adv;
+    const long long wa = ma - p.lg, wb = mb - p.lg;
+
+    for (int n = tid; n < M; n += NT) {
+        const double xa = src_read(src, ch, wa + n);
+        const double xb = has_b ? src_read(src, ch, wb + n) : 0.0;
+        zbuf[fft_pad(n)] = make_double2(xa, xb);
+    }
+    __syncthreads();
+    fft_forward<M, NT>(zbuf, p.tw, tid);
+
+    const long long t_lo = p.e0 * p.down, t_hi = p.e1 * p.down; // y indices [t_lo, t_hi) are wanted
+
+    if (UP == 1) {
+        for (int s = tid; s < M; s += NT) {
+            const double2 z = zbuf[fft_pad(s)];
+            const double2 g = __ldg(&p.spec[s]);
+            zbuf[fft_pad(s)] = cmul<+1>(z, g);
+        }
+        __syncthreads();
+        fft_inverse<M, NT>(zbuf, p.tw, tid);
+        const double* yb = reinterpret_cast<const double*>(zbuf);
+#pragma unroll 1
+        for (int which = 0; which < 2; which++) {
+            if (which == 1 && !has_b) break;
+            const long long mt = which ? mb : ma;
+            long long cnt = p.m1 - mt;
+            if (cnt > p.adv) cnt = p.adv;
+            for (int i = tid; i < cnt; i += NT) {
+                const long long t = mt + i;
+                if (t < t_lo || t >= t_hi) continue;
+                if (p.down > 1 && (t % p.down) != 0) continue;
+                dst_write(dst, ch, t / p.down, yb[2 * fft_pad(p.lg + i) + which]);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int which = 0; which < 2; which++) {
+            if (which == 1 && !has_b) break;
+            for (int s = tid; s < M; s += NT) {
+                const int k = freq_of<M>(s);
+                const int s2 = slot_of<M>((M - k) & (M - 1));
+                const double2 z1 = zbuf[fft_pad(s)];
+                const double2 z2 = zbuf[fft_pad(s2)];
+                double2 x;
+                if (which == 0) x = make_double2(z1.x + z2.x, z1.y - z2.y);       // z1 + conj z2
+                else x = make_double2(z1.y + z2.y, z2.x - z1.x);                  // -i (z1 - conj z2)
+                wbuf[fft_pad(s)] = cmul<+1>(x, __ldg(&p.spec[s]));
+            }
+            __syncthreads();
+            fft_inverse<M, NT>(wbuf, p.tw, tid);
+            const double* yb = reinterpret_cast<const double*>(wbuf);
+            const long long mt = which ? mb : ma;
+            long long cnt = p.m1 - mt;
+            if (cnt > p.adv) cnt = p.adv;
+            for (int i = tid; i < 2 * cnt; i += NT) {
+                const int ml = i >> 1, r = i & 1;
+                const long long t = 2 * (mt + ml) + r;
+                if (t < t_lo || t >= t_hi) continue;
+                if (p.down > 1 && (t % p.down) != 0) continue;
+                dst_write(dst, ch, t / p.down, yb[2 * fft_pad(p.lg + ml) + r]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+int blockconv_smem_bytes(int fft_log2, int up)
+{
+    const int m = 1 << fft_log2;
+    return fft_padded_len(m) * (int) sizeof(double2) * (up == 2 ? 2 : 1);
+}
+
+template <int M, int UP>
+static void launch_bc_inst(const BlockConvParams& p, const SrcView& src, const DstView& dst, int n_ch,
+                           cudaStream_t st)
+{
+    constexpr int NT = 256;
+    const int smem = blockconv_smem_bytes(p.fft_log2, UP);
+    static bool configured[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !configured[dev]) {
+        cudaFuncSetAttribute(k_blockconv<M, UP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured[dev] = true;
+    }
+    const int n_pairs = (p.n_tiles + 1) >> 1;
+    k_blockconv<M, UP, NT><<<(unsigned) (n_pairs * n_ch), NT, smem, st>>>(p, src, dst);
+}
+
+void launch_blockconv(const BlockConvParams& p, const SrcView& src, const DstView& dst, int n_ch,
+                      cudaStream_t st)
+{
+    if (p.n_tiles <= 0 || n_ch <= 0) return;
+    if (p.up == 1) {
+        switch (p.fft_log2) {
+        case 10: launch_bc_inst<1024, 1>(p, src, dst, n_ch, st); break;
+        case 11: launch_bc_inst<2048, 1>(p, src, dst, n_ch, st); break;
+        default: launch_bc_inst<4096, 1>(p, src, dst, n_ch, st); break;
+        }
+    } else {
+        switch (p.fft_log2) {
+        case 10: launch_bc_inst<1024, 2>(p, src, dst, n_ch, st); break;
+        case 11: launch_bc_inst<2048, 2>(p, src, dst, n_ch, st); break;
+        default: launch_bc_inst<4096, 2>(p, src, dst, n_ch, st); break;
+        }
+    }
+}
+
+cudaError_t blockconv_configure() { return cudaSuccess; }
+
+// ------------------------------------------------------------------------------------------
+// Fractional-delay interpolation, whole-number stepping: output j sits at input position
+// j*InStep/OutStep; the fractional part selects one of OutStep precomputed filters.
+__global__ void __launch_bounds__(256) k_frac_whole(FracParams p, SrcView src, DstView dst)
+{
+    const long long j = p.e0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.e1) return;
+    const int ch = blockIdx.y;
+    const long long pos = j * p.in_step;
+    const long long ip = pos / p.out_step;
+    const int phase = (int) (pos - ip * p.out_step);
+    const double* __restrict__ b = p.bank + (long long) phase * p.flen;
+    const long long x0 = ip - p.fll;
+    double acc = 0.0;
+    for (int i = 0; i < p.flen; i++) acc = fma(__ldg(b + i), src_read(src, ch, x0 + i), acc);
+    dst_write(dst, ch, j, acc);
+}
+
+void launch_frac_whole(const FracParams& p, const SrcView& src, const DstView& dst, int n_ch,
+                       cudaStream_t st)
+{
+    const long long n = p.e1 - p.e0;
+    if (n <= 0 || n_ch <= 0) return;
+    dim3 grid((unsigned) ((n + 255) / 256), (unsigned) n_ch);
+    k_frac_whole<<<grid, 256, 0, st>>>(p, src, dst);
+}
+
+// Non-whole stepping: bank of `fracs` filters, each tap a quadratic in the residual fraction.
+// The timing arithmetic reproduces the reference's IEEE expression order exactly
+// ((InCounter + InPosShift) * ssr) / dsr -- explicit _rn intrinsics forbid FMA contraction.
+__global__ void __launch_bounds__(256) k_frac_poly(FracParams p, SrcView src, DstView dst)
+{
+    const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long j = p.e0 + k;
+    if (j >= p.e1) return;
+    const int ch = blockIdx.y;
+    long long ip = p.p0;
+    double fpos = p.fpos0;
+    if (k > 0) {
+        const int ic = p.in_counter0 + (int) k;
+        const double np = __ddiv_rn(__dmul_rn(__dadd_rn((double) ic, p.in_pos_shift), p.ssr), p.dsr);
+        const int ni = __double2int_rz(np);
+        ip = p.p0 + (ni - p.in_pos_int0);
+        fpos = __dsub_rn(np, (double) ni);
+    }
+    double x = __dmul_rn(fpos, (double) p.fracs);
+    const int fti = __double2int_rz(x);
+    x = __dsub_rn(x, (double) fti);
+    const double x2 = __dmul_rn(x, x);
+    const double* __restrict__ b = p.bank + (long long) fti * p.flen * 3;
+    const long long x0 = ip - p.fll;
+    double acc = 0.0;
+    for (int i = 0; i < p.flen; i++) {
+        const double c = fma(__ldg(b + 3 * i + 2), x2, fma(__ldg(b + 3 * i + 1), x, __ldg(b + 3 * i)));
+        acc = fma(c, src_read(src, ch, x0 + i), acc);
+    }
+    dst_write(dst, ch, j, acc);
+}
+
+void launch_frac_poly(const FracParams& p, const SrcView& src, const DstView& dst, int n_ch,
+                      cudaStream_t st)
+{
+    const long long n = p.e1 - p.e0;
+    if (n <= 0 || n_ch <= 0) return;
+    dim3 grid((unsigned) ((n + 255) / 256), (unsigned) n_ch);
+    k_frac_poly<<<grid, 256, 0, st>>>(p, src, dst);
+}
+
+// ------------------------------------------------------------------------------------------
+// Half-band 2x upsampler: even outputs copy the input, odd outputs are the symmetric FIR.
+__global__ void __launch_bounds__(256) k_hbup(HbParams p, SrcView src, DstView dst)
+{
+    const long long n = (p.e0 >> 1) + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * n >= p.e1) return;
+    const int ch = blockIdx.y;
+    const double c = src_read(src, ch, n);
+    double acc = p.taps[0] * (src_read(src, ch, n + 1) + c);
+    for (int k = 1; k < p.ntaps; k++)
+        acc = fma(p.taps[k], src_read(src, ch, n + 1 + k) + src_read(src, ch, n - k), acc);
+    dst_write(dst, ch, 2 * n, c);
+    dst_write(dst, ch, 2 * n + 1, acc);
+}
+
+void launch_hbup(const HbParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
+{
+    const long long n = (p.e1 - p.e0) / 2;
+    if (n <= 0 || n_ch <= 0) return;
+    dim3 grid((unsigned) ((n + 255) / 256), (unsigned) n_ch);
+    k_hbup<<<grid, 256, 0, st>>>(p, src, dst);
+}
+
+// Half-band 2x decimator (gain 2, compensated by the following low-pass's gain).
+__global__ void __launch_bounds__(256) k_hbdown(HbParams p, SrcView src, DstView dst)
+{
+    const long long m = p.e0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= p.e1) return;
+    const int ch = blockIdx.y;
+    const long long c = 2 * m;
+    double acc = src_read(src, ch, c);
+    for (int k = 0; k < p.ntaps; k++)
+        acc = fma(p.taps[k], src_read(src, ch, c + 1 + 2 * k) + src_read(src, ch, c - 1 - 2 * k), acc);
+    dst_write(dst, ch, m, acc);
+}
+
+void launch_hbdown(const HbParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
+{
+    const long long n = p.e1 - p.e0;
+    if (n <= 0 || n_ch <= 0) return;
+    dim3 grid((unsigned) ((n + 255) / 256), (unsigned) n_ch);
+    k_hbdown<<<grid, 256, 0, st>>>(p, src, dst);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_save_tail(const double* __restrict__ cur, long long cur_stride,
+                                                   long long cur_base, long long n0, long long n1,
+                                                   double* __restrict__ ring, long long ring_stride,
+                                                   long long ring_mask)
+{
+    const long long n = n0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n1) return;
+    const int ch = blockIdx.y;
+    ring[(long long) ch * ring_stride + (n & ring_mask)] = cur[(long long) ch * cur_stride + (n - cur_base)];
+}
+
+void launch_save_tail(const double* cur, long long cur_stride, long long cur_base, long long n0,
+                      long long n1, double* ring, long long ring_stride, long long ring_mask, int n_ch,
+                      cudaStream_t st)
+{
+    const long long n = n1 - n0;
+    if (n <= 0 || n_ch <= 0) return;
+    dim3 grid((unsigned) ((n + 255) / 256), (unsigned) n_ch);
+    k_save_tail<<<grid, 256, 0, st>>>(cur, cur_stride, cur_base, n0, n1, ring, ring_stride, ring_mask);
+}
+
+} // namespace r8bgpu

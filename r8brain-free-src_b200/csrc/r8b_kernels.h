@@ -1,0 +1,78 @@
+// r8b_kernels.h -- launch interface between the host engine (r8b_engine.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace r8bgpu {
+
+// A per-channel sample stream addressed by ABSOLUTE sample index n (n = 0 is the first sample
+// after clear()).  Samples with n >= cur_base are read from the caller's block of this
+// process() call; older samples come from a power-of-two ring that holds the recent past.
+// Indices < 0 land in ring slots that are still zero (rings are cleared at clear()).
+struct SrcView {
+    const double* ring;    // [n_ch][ring_stride]
+    long long ring_stride;
+    long long ring_mask;   // capacity-1
+    const double* cur;     // [n_ch][cur_stride] or nullptr
+    long long cur_stride;
+    long long cur_base;    // absolute index of cur[0]; LLONG_MAX when there is no cur block
+    long long avail;       // samples with n >= avail do not exist yet (read as 0)
+};
+
+// Destination stream: either a ring (mask = capacity-1, base = 0) or a linear block whose
+// element 0 is absolute index `base` (mask = -1).
+struct DstView {
+    double* ptr;           // [n_ch][stride]
+    long long stride;
+    long long mask;
+    long long base;
+};
+
+struct BlockConvParams {
+    int up, down;
+    int lg;                // half support of the polyphase filters, in input samples
+    int fft_log2;          // log2(M)
+    int adv;               // valid input-rate positions per tile (<= M - 2*lg)
+    long long m0, m1;      // input-rate positions [m0,m1) whose outputs may be needed
+    long long e0, e1;      // output indices to write
+    int n_tiles;
+    const double2* spec;   // filter spectrum in slot order, pre-scaled (device)
+    const double2* tw;     // twiddles exp(-2*pi*i*k/M) (device)
+};
+
+struct FracParams {
+    int flen, fll;
+    long long e0, e1;
+    const double* bank;    // device; [(fracs+1)][flen][order+1]
+    // whole stepping
+    int in_step, out_step;
+    // polynomial (order 2)
+    int fracs;
+    double ssr, dsr;
+    int in_counter0, in_pos_int0;
+    double in_pos_shift, fpos0;
+    long long p0;
+};
+
+struct HbParams {
+    int ntaps;
+    long long e0, e1;
+    double taps[14];
+};
+
+int blockconv_smem_bytes(int fft_log2, int up);
+cudaError_t blockconv_configure(); // opt-in shared memory attributes; call once per device
+
+void launch_blockconv(const BlockConvParams& p, const SrcView& src, const DstView& dst, int n_ch,
+                      cudaStream_t st);
+void launch_frac_whole(const FracParams& p, const SrcView& src, const DstView& dst, int n_ch,
+                       cudaStream_t st);
+void launch_frac_poly(const FracParams& p, const SrcView& src, const DstView& dst, int n_ch,
+                      cudaStream_t st);
+void launch_hbup(const HbParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st);
+void launch_hbdown(const HbParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st);
+// copy cur[n0..n1) into the ring (history for later calls)
+void launch_save_tail(const double* cur, long long cur_stride, long long cur_base, long long n0,
+                      long long n1, double* ring, long long ring_stride, long long ring_mask, int n_ch,
+                      cudaStream_t st);
+
+} // namespace r8bgpu
