@@ -1,0 +1,328 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the CDSPResampler::process() path on B200.
+
+Metric (BASELINE.json / SURVEY.md section 8d): input Msamples/s = 1e-6 * frames * channels / seconds
+inside process() -- the reference's "Mrops" (bench/r8bfreesrc.cpp:95,140-141).
+
+A "step" is one process() call over one batch: `channels` independent fp64 streams, `block`
+(=65536, the reference's MaxInLen in BASELINE's configs) new samples each.  The default workload is
+BASELINE configs[1]: 1024 channels, 44100 -> 96000, CDSPResampler24 (2 % transition band).
+
+  value      inputs already resident in HBM, K steps timed with CUDA events on the launch stream
+  e2e        the same K steps through r8bgpu_batch_process_host(): pinned HOST buffers, H2D of the
+             block and D2H of the produced samples inside the timed region
+  roofline   dominant kernel's algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own CPU path (oracle/_ref, R8B_PFFFT_DOUBLE, -O3 -mavx2 -mfma) on all
+             host threads over a bounded sample of the same workload
+
+N > 1 (torchrun): channels are sharded over ranks (weak scaling: `channels` per GPU), no data-path
+collective; barrier + synchronize on both sides, max over ranks.
+
+--impl reference: times ONLY the reference CPU implementation (rank 0), same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (src, dst, atten, tb, extfft, default channels per GPU)
+    "cfg2_1024ch_44100_96000_r24": (44100.0, 96000.0, 180.15, 2.0, 0, 1024),
+    "cfg3_1024ch_48000_44100_r24": (48000.0, 44100.0, 180.15, 2.0, 0, 1024),
+    "cfg5_512ch_48000_47999_r24": (48000.0, 47999.0, 180.15, 2.0, 0, 512),
+    "cfg4_128ch_44100_2822400_r24_extfft": (44100.0, 2822400.0, 180.15, 2.0, 1, 128),
+    "cfg3b_1024ch_192000_44100_r24": (192000.0, 44100.0, 180.15, 2.0, 0, 1024),
+}
+DEFAULT_WORKLOAD = "cfg2_1024ch_44100_96000_r24"
+BLOCK = 65536
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [t.strip() for t in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_block(n_ch, block, seed):
+    """Planar fp64 white noise in [-1,1), per-channel stream."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1.0, 1.0, size=(n_ch, block))
+
+
+def cpu_reference_run(src, dst, tb, atten, extfft, threads, target_seconds=8.0):
+    """Time the compiled reference (oracle/_ref) on host cores over a bounded sample."""
+    import oracle_util as ou
+    flavor = ("e1" if extfft else "e0") + ("_fast" if ou.cpu_supports_fast() and ou.have_ref(("e1" if extfft else "e0") + "_fast") else "")
+    if not ou.have_ref(flavor):
+        return None
+    ref = ou.RefOracle(flavor)
+    n_ch = max(1, threads) * 2
+    x = synth_block(n_ch, BLOCK, 99)
+    # calibrate with 1 call, then size the sample to ~target_seconds of wall time
+    t1, _, _ = ref.bench(src, dst, BLOCK, tb, atten, x, 1, 1, threads)
+    calls = int(max(2, min(256, target_seconds / max(t1, 1e-4))))
+    secs, n_out, _ = ref.bench(src, dst, BLOCK, tb, atten, x, 1, calls, threads)
+    val = 1e-6 * n_ch * BLOCK * calls / secs
+    return {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "reference",
+            "sample": "%d ch x %d calls x %d frames, %s, %d threads, %.2f s" % (n_ch, calls, BLOCK, ref.name, threads, secs),
+            "ms_per_step_equiv": secs / calls * 1e3, "n_ch": n_ch, "calls": calls, "secs": secs}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--channels", type=int, default=0, help="channels per GPU (default: the workload's)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    src, dst, atten, tb, extfft, def_ch = WORKLOADS[args.workload]
+    n_ch = args.channels or def_ch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3)
+    threads = os.cpu_count() or 1
+    config = {"workload": args.workload, "src_rate": src, "dst_rate": dst, "preset": "CDSPResampler24",
+              "trans_band_pct": tb, "channels_per_gpu": n_ch, "block_frames": BLOCK, "extfft": extfft,
+              "parallelism": "channels sharded over %d GPU(s), no data-path collective" % world,
+              "l2_policy": "per-step input (%.0f MB) and output exceed the 126 MB L2" % (n_ch * BLOCK * 8 / 1e6)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(src, dst, tb, atten, extfft, threads,
+                              target_seconds=max(2.0, min(20.0, 0.5 * (K + W))))
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (no /root/reference at build time)"}))
+            return 0
+        line = {"impl": "reference", "metric": "input Msamples/s (Mrops), fp64 %g->%g" % (src, dst),
+                "value": r["value"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": r["ms_per_step_equiv"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    if not torch.cuda.is_available() or pkg.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    plan = pkg.Plan(src, dst, BLOCK, tb, atten, extfft=extfft)
+    batch = pkg.Batch(plan, n_ch, local_rank)
+    cap = plan.max_out_len
+    # Two distinct input blocks alternate so that no step re-reads a block that could sit in L2.
+    xs = [torch.from_numpy(synth_block(n_ch, BLOCK, 1000 + 17 * rank + i)).to(dev) for i in range(2)]
+    out = torch.empty((n_ch, cap), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    batch.set_stream(stream.cuda_stream)
+
+    def step(i):
+        return batch.process_ptr(xs[i & 1].data_ptr(), BLOCK, BLOCK, out.data_ptr(), cap, cap)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # samples every 100 ms through warm-up and the timed region (both under load)
+    for i in range(W):
+        step(i)
+    barrier()
+    # keep the GPU under the same load until nvidia-smi has produced a few rows
+    t_load = time.perf_counter()
+    j = 0
+    while rank == 0 and len(sampler.rows) < 3 and time.perf_counter() - t_load < 3.0:
+        step(W + j)
+        j += 1
+        torch.cuda.synchronize(dev)
+    sampler.rows = sampler.rows[-1:] if sampler.rows else []
+    l0 = batch.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    n_out_total = 0
+    for i in range(K):
+        n_out_total += step(W + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = batch.kernel_launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = 1e-6 * world * n_ch * BLOCK * K / (ms * 1e-3)
+
+    # ---- per-stage device time (separate pass; events around every stage launch)
+    batch.set_timing(True)
+    for i in range(K):
+        step(i)
+    st_times = batch.stage_times()
+    batch.set_timing(False)
+    stage_info = plan.stages()
+    tot_stage_ms = sum(t[1] for t in st_times) or 1.0
+    dom = max(range(len(st_times)), key=lambda i: st_times[i][1])
+    # algorithmic bytes of the dominant kernel per launch: its own input + output streams
+    rate = [1.0]
+    for s in stage_info:
+        prev = rate[-1]
+        if s["name"] == "blockconv":
+            rate.append(prev * s["up"] / s["down"])
+        elif s["name"] == "hbup":
+            rate.append(prev * 2)
+        elif s["name"] == "hbdown":
+            rate.append(prev / 2)
+        else:
+            rate.append(dst / src)  # interpolator lands on the chain's final ratio at that point
+    # fix interpolator rates for chains where more stages follow (use exact plan ratios)
+    for i, s in enumerate(stage_info):
+        if s["name"].startswith("frac"):
+            tail = 1.0
+            for t in stage_info[i + 1:]:
+                tail *= (t["up"] / t["down"]) if t["name"] == "blockconv" else (2 if t["name"] == "hbup" else 0.5 if t["name"] == "hbdown" else 1.0)
+            rate[i + 1] = (dst / src) / tail
+    dom_bytes = 8.0 * n_ch * BLOCK * (rate[dom] + rate[dom + 1])
+    dom_ms = st_times[dom][1] / max(1, st_times[dom][2])
+    peak, peak_src = measured_peaks()
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    path_bytes_per_in = 8.0 * (1.0 + dst / src)
+    roofline = {"bound": "hbm", "kernel": "k_" + st_times[dom][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+                "kernel_share_of_step": st_times[dom][1] / tot_stage_ms,
+                "stage_ms_per_step": {("%d:%s" % (i, t[0])): t[1] / K for i, t in enumerate(st_times)},
+                "path": {"algorithmic_bytes_per_in_sample": path_bytes_per_in,
+                         "achieved": path_bytes_per_in * value * 1e6 / world / 1e9,
+                         "frac": path_bytes_per_in * value * 1e6 / world / 1e9 / peak}}
+
+    # ---- end to end through the host-pointer C-ABI call (pinned host buffers)
+    e2e = None
+    if not args.no_e2e:
+        hx = [torch.from_numpy(synth_block(n_ch, BLOCK, 2000 + i)).pin_memory() for i in range(2)]
+        hy = torch.empty((n_ch, cap), dtype=torch.float64).pin_memory()
+        batch.set_stream(None)
+        ke = max(3, min(K, 8))
+        for i in range(2):
+            batch.process_host_ptr(hx[i & 1].data_ptr(), BLOCK, BLOCK, hy.data_ptr(), cap, cap)
+        barrier()
+        t0 = time.perf_counter()
+        outs = 0
+        for i in range(ke):
+            outs += batch.process_host_ptr(hx[i & 1].data_ptr(), BLOCK, BLOCK, hy.data_ptr(), cap, cap)
+        torch.cuda.synchronize(dev)
+        t_e2e = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": 1e-6 * world * n_ch * BLOCK * ke / t_e2e, "unit": "Msamples/s",
+               "h2d_bytes_per_step": n_ch * BLOCK * 8, "d2h_bytes_per_step": int(n_ch * (outs / ke) * 8),
+               "steps": ke, "api": "r8bgpu_batch_process_host (pinned host in/out, sync per call)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_run(src, dst, tb, atten, extfft, threads, target_seconds=8.0)
+        if r is not None:
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "input Msamples/s (Mrops), fp64 %g->%g" % (src, dst), "value": value, "unit": "Msamples/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": (value / 38.0 if (src, dst) == (44100.0, 96000.0) else None),
+                "vs_baseline_note": "published: 38 Mrops per core (Ooura FFT, Ryzen 3700X), README.md:111-114",
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "out_msamples_per_s": 1e-6 * world * n_ch * n_out_total / (ms * 1e-3),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "device_state_bytes": batch.device_bytes}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

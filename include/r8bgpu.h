@@ -127,6 +127,11 @@ R8BGPU_API int r8bgpu_batch_process_host(r8bgpu_batch* batch, const double* h_in
 R8BGPU_API int r8bgpu_batch_sync(r8bgpu_batch* batch);
 /* Number of kernels this batch has launched since creation. */
 R8BGPU_API unsigned long long r8bgpu_batch_kernel_launches(const r8bgpu_batch* batch);
+/* Per-stage device timing for profiling/bench: when enabled every stage launch is bracketed
+ * by CUDA events on the batch's stream.  r8bgpu_batch_stage_time_ms() synchronises and returns the
+ * accumulated milliseconds (and launch count) of one stage since timing was (re-)enabled. */
+R8BGPU_API int r8bgpu_batch_set_timing(r8bgpu_batch* batch, int enable);
+R8BGPU_API double r8bgpu_batch_stage_time_ms(r8bgpu_batch* batch, int stage, unsigned long long* launches);
 /* Bytes of device memory held by the batch (state rings + tables + staging). */
 R8BGPU_API unsigned long long r8bgpu_batch_device_bytes(const r8bgpu_batch* batch);
 

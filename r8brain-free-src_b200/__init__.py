@@ -65,6 +65,8 @@ _SYMBOLS = {
     "r8bgpu_batch_sync": (C.c_int, [C.c_void_p]),
     "r8bgpu_batch_kernel_launches": (C.c_ulonglong, [C.c_void_p]),
     "r8bgpu_batch_device_bytes": (C.c_ulonglong, [C.c_void_p]),
+    "r8bgpu_batch_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "r8bgpu_batch_stage_time_ms": (C.c_double, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]),
     "r8bgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
     "r8bgpu_host_free": (None, [C.c_void_p]),
 }
@@ -210,6 +212,20 @@ class Batch:
     @property
     def device_bytes(self):
         return int(lib().r8bgpu_batch_device_bytes(self._h))
+
+    def set_timing(self, enable=True):
+        lib().r8bgpu_batch_set_timing(self._h, int(bool(enable)))
+
+    def stage_times(self):
+        """[(stage_name, accumulated_ms, launches)] since set_timing(True); synchronises."""
+        out = []
+        for i, st in enumerate(self.plan.stages()):
+            n = C.c_ulonglong(0)
+            ms = lib().r8bgpu_batch_stage_time_ms(self._h, i, C.byref(n))
+            if ms < 0:
+                raise R8bGpuError(_err())
+            out.append((st["name"], ms, int(n.value)))
+        return out
 
     def process_ptr(self, d_in, in_stride, l, d_out, out_stride, out_cap):
         """Raw device-pointer call (asynchronous).  Returns samples produced per channel."""

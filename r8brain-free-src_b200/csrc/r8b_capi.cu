@@ -71,7 +71,7 @@ void fill_slot_order(const std::vector<double2>& nat, std::vector<double2>& out)
 }
 
 void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec_slots,
-                    std::vector<double2>& tw)
+                    std::vector<double2>& tw, double* nyq_gain)
 {
     const int M = 1 << fft_log2;
     const int L = s.lp.half_len, U = s.up;
@@ -107,6 +107,16 @@ void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec
         }
         nat[(size_t) k] = make_double2((double) (re * scale), (double) (im * scale));
     }
+    if (s.block_exact) {
+        // Power-of-two decimation in the reference = inverse transform of only the lowest 1/D of
+        // the block spectrum (CDSPBlockConvolver.h:329-344).  Same thing here: the bins that the
+        // shorter inverse FFT never sees are zeroed and the full-length inverse is sampled every
+        // D-th point.  (The folded Nyquist term kb[z]*p[z]-kb[z+1]*p[z+1] is the product of two
+        // stop-band values, far below one ulp of the output, and is dropped.)
+        const int keep = M / (2 * s.down);
+        if (nyq_gain) *nyq_gain = nat[(size_t) keep].x;
+        for (int k = keep; k <= M - keep; k++) nat[(size_t) k] = make_double2(0.0, 0.0);
+    }
     switch (fft_log2) {
     case 10: fill_slot_order<1024>(nat, spec_slots); break;
     case 11: fill_slot_order<2048>(nat, spec_slots); break;
@@ -138,6 +148,7 @@ int choose_fft_log2(int lg)
 struct StageDev {
     // BLOCKCONV
     int fft_log2 = 0, lg = 0;
+    double nyq_gain = 0.0;
     double2* spec = nullptr;
     double2* tw = nullptr;
     // FRAC
@@ -164,6 +175,15 @@ struct r8bgpu_batch {
     std::vector<StageCall> calls;
     unsigned long long launches = 0;
     unsigned long long dev_bytes = 0;
+    // optional per-stage device timing (CUDA events on the launch stream)
+    bool timing = false;
+    struct EvPair {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<EvPair> events;
+    std::vector<double> stage_ms;
+    std::vector<unsigned long long> stage_launches;
     // staging for the host-pointer entry point
     double* st_in = nullptr;
     double* st_out = nullptr;
@@ -362,12 +382,17 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
             }
             d.lg = (s.lp.half_len + s.up - 1) / s.up;
             d.fft_log2 = choose_fft_log2(d.lg);
+            if (s.block_exact) { // tiles == the reference's own blocks
+                d.lg = s.ref_prev_len - s.lp.half_len;
+                d.fft_log2 = s.lp.block_len_bits + 1;
+                if (d.fft_log2 < 10 || d.fft_log2 > 12) d.fft_log2 = -1;
+            }
             if (d.fft_log2 < 0) {
                 set_err("batch_create: low-pass kernel too long for the in-shared-memory FFT tiles");
                 return nullptr;
             }
             std::vector<double2> spec, tw;
-            build_spectrum(s, d.fft_log2, spec, tw);
+            build_spectrum(s, d.fft_log2, spec, tw, &d.nyq_gain);
             const size_t nb = spec.size() * sizeof(double2);
             if (!cuda_ok(cudaMalloc(&d.spec, nb), "cudaMalloc(spec)")) return nullptr;
             if (!cuda_ok(cudaMalloc(&d.tw, nb), "cudaMalloc(tw)")) return nullptr;
@@ -393,6 +418,44 @@ void r8bgpu_batch_destroy(r8bgpu_batch* batch) { delete batch; }
 int r8bgpu_batch_channels(const r8bgpu_batch* b) { return b->n_ch; }
 unsigned long long r8bgpu_batch_kernel_launches(const r8bgpu_batch* b) { return b->launches; }
 unsigned long long r8bgpu_batch_device_bytes(const r8bgpu_batch* b) { return b->dev_bytes; }
+
+int r8bgpu_batch_set_timing(r8bgpu_batch* b, int enable)
+{
+    DeviceGuard g(b->device);
+    for (auto& e : b->events) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    b->events.clear();
+    b->stage_ms.assign(b->plan->stages.size(), 0.0);
+    b->stage_launches.assign(b->plan->stages.size(), 0);
+    b->timing = enable != 0;
+    return 0;
+}
+
+// Synchronises the stream, folds the pending event pairs into per-stage totals and returns the
+// accumulated device time (ms) of `stage` since timing was enabled; *launches = kernel launches.
+double r8bgpu_batch_stage_time_ms(r8bgpu_batch* b, int stage, unsigned long long* launches)
+{
+    if (stage < 0 || stage >= (int) b->stage_ms.size()) {
+        set_err("stage_time_ms: timing not enabled or bad stage");
+        return -1.0;
+    }
+    DeviceGuard g(b->device);
+    if (!cuda_ok(cudaStreamSynchronize(b->stream), "stage_time_ms: sync")) return -1.0;
+    for (auto& e : b->events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            b->stage_ms[(size_t) e.stage] += ms;
+            b->stage_launches[(size_t) e.stage]++;
+        }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    b->events.clear();
+    if (launches) *launches = b->stage_launches[(size_t) stage];
+    return b->stage_ms[(size_t) stage];
+}
 
 int r8bgpu_batch_set_stream(r8bgpu_batch* b, void* stream)
 {
@@ -485,6 +548,12 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
             dst.mask = b->dev[i + 1].ring_cap - 1;
             dst.base = 0;
         }
+        r8bgpu_batch::EvPair ev{(int) i, nullptr, nullptr};
+        if (b->timing) {
+            cudaEventCreate(&ev.a);
+            cudaEventCreate(&ev.b);
+            cudaEventRecord(ev.a, st);
+        }
         switch (s.kind) {
         case ST_BLOCKCONV: {
             BlockConvParams p;
@@ -496,12 +565,23 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
             p.e1 = c.e1;
             p.m0 = (c.e0 * s.down) / s.up;               // floor; indices are >= 0
             p.m1 = ((c.e1 - 1) * s.down) / s.up + 1;
-            const int adv_max = (1 << d.fft_log2) - 2 * d.lg;
-            const long long span = p.m1 - p.m0;
-            long long nt = (span + adv_max - 1) / adv_max;
-            if (nt > 1 && (nt & 1)) nt++; // tiles are transformed in pairs
-            p.n_tiles = (int) nt;
-            p.adv = (int) ((span + nt - 1) / nt);
+            if (s.block_exact) {
+                // tile b = reference block b: owns positions [b*InputLen - L, (b+1)*InputLen - L)
+                const long long il = s.ref_input_len, L = s.lp.half_len;
+                const long long b0 = (p.m0 + L) / il, b1 = (p.m1 - 1 + L) / il;
+                p.m0 = b0 * il - L;
+                p.adv = (int) il;
+                p.n_tiles = (int) (b1 - b0 + 1);
+            } else {
+                const int adv_max = (1 << d.fft_log2) - 2 * d.lg;
+                const long long span = p.m1 - p.m0;
+                long long nt = (span + adv_max - 1) / adv_max;
+                if (nt > 1 && (nt & 1)) nt++; // tiles are transformed in pairs
+                p.n_tiles = (int) nt;
+                p.adv = (int) ((span + nt - 1) / nt);
+            }
+            p.trunc = s.block_exact ? s.down : 0;
+            p.nyq_gain = d.nyq_gain;
             p.spec = d.spec;
             p.tw = d.tw;
             launch_blockconv(p, src, dst, b->n_ch, st);
@@ -545,6 +625,10 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
             b->launches++;
             break;
         }
+        }
+        if (b->timing) {
+            cudaEventRecord(ev.b, st);
+            b->events.push_back(ev);
         }
     }
     // Keep the most recent input samples for the next calls.

@@ -75,10 +75,26 @@ __global__ void __launch_bounds__(NT) k_blockconv(BlockConvParams p, SrcView src
     const long long t_lo = p.e0 * p.down, t_hi = p.e1 * p.down; // y indices [t_lo, t_hi) are wanted
 
     if (UP == 1) {
+        // Power-of-two decimation, reference-exact: the short inverse FFT of the reference sees the
+        // low 1/D of the spectrum (spec[] is zero elsewhere) plus one real "Nyquist" value
+        // kb[z]*p[z] - kb[z+1]*p[z+1] = H(fs/2D) * (Re X - Im X) (CDSPBlockConvolver.h:329-342 with the
+        // zero-phase kernel layout).  In the full-length inverse sampled at multiples of D that value
+        // is a component at bin M/(2D); for the packed pair it is (c_a + i*c_b).
+        __shared__ double2 nyq;
+        const int kq = M / (2 * (p.trunc > 0 ? p.trunc : 1));
+        if (p.trunc > 0 && tid == 0) {
+            const double2 z1 = zbuf[fft_pad(slot_of<M>(kq))];
+            const double2 z2 = zbuf[fft_pad(slot_of<M>(M - kq))];
+            const double2 xa = make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y));
+            const double2 xb = make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x));
+            nyq = make_double2(p.nyq_gain * (xa.x - xa.y), p.nyq_gain * (xb.x - xb.y));
+        }
+        if (p.trunc > 0) __syncthreads();
+        const int sq = slot_of<M>(kq);
         for (int s = tid; s < M; s += NT) {
             const double2 z = zbuf[fft_pad(s)];
             const double2 g = __ldg(&p.spec[s]);
-            zbuf[fft_pad(s)] = cmul<+1>(z, g);
+            zbuf[fft_pad(s)] = (p.trunc > 0 && s == sq) ? nyq : cmul<+1>(z, g);
         }
         __syncthreads();
         fft_inverse<M, NT>(zbuf, p.tw, tid);

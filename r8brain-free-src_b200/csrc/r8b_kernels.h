@@ -35,6 +35,8 @@ struct BlockConvParams {
     long long m0, m1;      // input-rate positions [m0,m1) whose outputs may be needed
     long long e0, e1;      // output indices to write
     int n_tiles;
+    int trunc;             // 0, or D for reference-exact power-of-two decimation (see k_blockconv)
+    double nyq_gain;       // scaled filter response at bin M/(2D) (trunc only)
     const double2* spec;   // filter spectrum in slot order, pre-scaled (device)
     const double2* tw;     // twiddles exp(-2*pi*i*k/M) (device)
 };

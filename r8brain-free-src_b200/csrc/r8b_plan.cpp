@@ -45,13 +45,17 @@ bool make_blockconv(StageDesc& s, double norm_freq, double tb, double atten, dou
             return false;
         }
         const int ilc = in_len & (down - 1);
+        prev_len += ilc;
         in_len -= ilc;
         latency -= ilc;
+        s.block_exact = true;
     }
     s.ref_input_len = in_len;
+    s.ref_prev_len = prev_len;
     s.latency = latency;
     const int lg = (L + up - 1) / up + 1;
     s.src_history = (latency + L + up - 1) / up + lg + 8;
+    if (s.block_exact) s.src_history = 2 * b2 + 16;
     return true;
 }
 

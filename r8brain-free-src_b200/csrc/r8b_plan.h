@@ -37,6 +37,11 @@ struct StageDesc {
     int up = 1, down = 1;
     int ref_input_len = 0;   // the reference's InputLen (emission timing only)
     int latency = 0;         // the reference's Latency = InputLen + L
+    int ref_prev_len = 0;    // the reference's PrevInputLen (overlap carried between its blocks)
+    bool block_exact = false; // power-of-two D: the reference inverse-transforms only the lower
+                             // 1/D of each block spectrum (CDSPBlockConvolver.h:329-344), which is
+                             // NOT plain decimation; such stages reproduce the reference's block
+                             // segmentation (FFT size 2<<BlockLenBits, blocks every InputLen).
     double norm_freq = 0, trans_band = 0, gain = 0;
     LowpassDesign lp;
     // --- Frac

@@ -1,0 +1,162 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the compiled reference oracle.
+
+Tolerance: per channel, max|d| <= 32*eps*max|y| and rms(d) <= 4*eps*rms(y),
+eps = 2^-52, with per-call output counts EXACTLY equal.  The reference disagrees with itself at
+the 10-eps level between FFT back-ends, so bit equality is not defined for this path.
+"""
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+pytestmark = pytest.mark.gpu
+
+MAX_TOL = 32 * ou.EPS
+RMS_TOL = 4 * ou.EPS
+
+
+def run_both(pkg, oracle, src, dst, lens, n_ch=3, tb=2.0, atten=180.15, extfft=0, seed=1, max_in=None):
+    max_in = max_in or max(lens)
+    x = ou.white_noise(n_ch, int(sum(lens)), seed)
+    rb = pkg.ResamplerBatch(n_ch, src, dst, max_in, tb, atten, device=0, extfft=extfft)
+    rs = [oracle.Resampler(src, dst, max_in, tb, atten) for _ in range(n_ch)]
+    pos = 0
+    ys, yr = [[] for _ in range(n_ch)], [[] for _ in range(n_ch)]
+    for l in lens:
+        y = rb.process(x[:, pos:pos + l])
+        for c in range(n_ch):
+            r = rs[c].process(x[c, pos:pos + l])
+            assert len(r) == y.shape[1], "per-call count differs: ref %d gpu %d (l=%d)" % (len(r), y.shape[1], l)
+            ys[c].append(y[c])
+            yr[c].append(r)
+        pos += l
+    return [np.concatenate(a) for a in ys], [np.concatenate(a) for a in yr]
+
+
+def check(ys, yr, max_tol=MAX_TOL, rms_tol=RMS_TOL):
+    worst = (0.0, 0.0)
+    for a, b in zip(ys, yr):
+        assert len(a) == len(b) and len(a) > 0
+        m, r = ou.parity_metrics(a, b)
+        worst = (max(worst[0], m), max(worst[1], r))
+        assert m <= max_tol, "max err %.3g eps" % (m / ou.EPS)
+        assert r <= rms_tol, "rms err %.3g eps" % (r / ou.EPS)
+    return worst
+
+
+CHAINS = [
+    (44100.0, 96000.0),    # BASELINE cfg 1/2: BlockConv 2x -> whole-step interp 147/160
+    (48000.0, 44100.0),    # cfg 3: BlockConv 2x (NormFreq .459) -> whole-step 320/147
+    (48000.0, 47999.0),    # cfg 5: BlockConv 2x -> order-2 interpolated bank
+    (44100.0, 88200.0),    # BlockConv 2x only
+    (44100.0, 176400.0),   # BlockConv 2x -> HBUp
+    (192000.0, 44100.0),   # HBDown -> BlockConv 1/1 -> whole-step
+    (96000.0, 48000.0),    # BlockConv 1/2
+    (48000.0, 16000.0),    # BlockConv 1/3
+    (44100.0, 192000.0),   # BlockConv -> interp -> BlockConv -> HBUp (intermediate interpolation)
+    (44100.0, 22050.5),    # fractional downsampling just above 2x
+]
+
+
+@pytest.mark.parametrize("src,dst", CHAINS)
+def test_chain_parity(pkg, ref, src, dst):
+    ys, yr = run_both(pkg, ref, src, dst, [8192] * 4 + [1000, 1, 0, 17, 8192], max_in=8192)
+    w = check(ys, yr)
+    print("%g->%g: max %.2f eps, rms %.2f eps" % (src, dst, w[0] / ou.EPS, w[1] / ou.EPS))
+
+
+def test_dsd_cascade_extfft(pkg, ref_e1):
+    # cfg 4: 44100 -> 2822400 with R8B_EXTFFT=1: BlockConv 2x -> HBUp x5
+    ys, yr = run_both(pkg, ref_e1, 44100.0, 2822400.0, [2048] * 5 + [100], n_ch=2, extfft=1, max_in=2048)
+    check(ys, yr)
+
+
+def test_hbdown_cascade(pkg, ref):
+    ys, yr = run_both(pkg, ref, 2822400.0, 44100.0, [65536] * 8, n_ch=2, max_in=65536)
+    check(ys, yr)
+
+
+def test_full_block_size(pkg, ref):
+    # BASELINE block size: 65536-sample calls, counts 138963, 142664, 142663 ...
+    ys, yr = run_both(pkg, ref, 44100.0, 96000.0, [65536] * 3, n_ch=2)
+    assert len(ys[0]) == 138963 + 142664 + 142663
+    check(ys, yr)
+
+
+def test_presets_and_transition_bands(pkg, ref):
+    for atten in (pkg.ATTEN_16, pkg.ATTEN_16IR, 206.91):
+        for tb in (2.0, 5.0):
+            ys, yr = run_both(pkg, ref, 44100.0, 48000.0, [4096] * 6, n_ch=1, tb=tb, atten=atten)
+            check(ys, yr)
+
+
+def test_chunking_invariance(pkg):
+    # Whole-stepping chains: the same stream fed in different block sizes gives the same output to
+    # rounding (the reference is bit-invariant; our FFT tiles are anchored per call).
+    x = ou.white_noise(2, 40000, 7)
+    outs = []
+    for lens in ([40000], [4096] * 9 + [3136], [1000] * 40, [1] * 50 + [39950]):
+        rb = pkg.ResamplerBatch(2, 44100.0, 96000.0, 40000, 2.0, pkg.ATTEN_24, device=0)
+        pos, acc = 0, []
+        for l in lens:
+            acc.append(rb.process(x[:, pos:pos + l]))
+            pos += l
+        outs.append(np.concatenate(acc, axis=1))
+    for o in outs[1:]:
+        assert o.shape == outs[0].shape
+        m, r = ou.parity_metrics(o[0], outs[0][0])
+        assert m <= MAX_TOL and r <= RMS_TOL
+
+
+def test_clear_restarts_stream(pkg, ref):
+    x = ou.white_noise(1, 20000, 3)
+    rb = pkg.ResamplerBatch(1, 44100.0, 96000.0, 20000, device=0)
+    a = rb.process(x)
+    rb.clear()
+    b = rb.process(x)
+    assert np.array_equal(a, b)
+
+
+def test_zero_input_gives_zero_output(pkg):
+    rb = pkg.ResamplerBatch(2, 48000.0, 47999.0, 8192, device=0)
+    y = rb.process(np.zeros((2, 8192)))
+    assert y.shape[1] > 0 and not np.any(y)
+
+
+def test_impulse_and_dc_gain(pkg):
+    # unity DC gain end to end (filter gain = upsampling factor, bank rows sum to 1)
+    rb = pkg.ResamplerBatch(1, 44100.0, 96000.0, 16384, device=0)
+    y = np.concatenate([rb.process(np.ones((1, 16384)))[0] for _ in range(2)])
+    assert abs(y[-1000:].mean() - 1.0) < 1e-13
+
+
+def test_device_pointer_api_and_strides(pkg, ref):
+    import torch
+    n_ch, l = 5, 6000
+    x = ou.white_noise(n_ch, l * 2, 11)
+    plan = pkg.Plan(44100.0, 96000.0, l, 2.0, pkg.ATTEN_24)
+    b = pkg.Batch(plan, n_ch, 0)
+    xin = torch.zeros((n_ch, 2 * l + 13), dtype=torch.float64, device="cuda:0")  # padded stride
+    xin[:, :2 * l] = torch.from_numpy(x).cuda()
+    out = torch.empty((n_ch, plan.max_out_len + 5), dtype=torch.float64, device="cuda:0")
+    got = []
+    for c in range(2):
+        y = b.process(xin[:, c * l:(c + 1) * l], out)
+        got.append(y.cpu().numpy().copy())
+    got = np.concatenate(got, axis=1)
+    for c in range(n_ch):
+        r = ref.Resampler(44100.0, 96000.0, l, 2.0, pkg.ATTEN_24)
+        yr = np.concatenate([r.process(x[c, :l]), r.process(x[c, l:])])
+        assert len(yr) == got.shape[1]
+        m, rr = ou.parity_metrics(got[c], yr)
+        assert m <= MAX_TOL and rr <= RMS_TOL
+    assert b.kernel_launches > 0
+
+
+def test_errors_are_loud(pkg):
+    plan = pkg.Plan(44100.0, 96000.0, 1024)
+    b = pkg.Batch(plan, 1, 0)
+    with pytest.raises(pkg.R8bGpuError):
+        b.process_host(np.zeros((1, 2048)))  # l > MaxInLen
+    with pytest.raises(pkg.R8bGpuError):
+        pkg.Plan(44100.0, 96000.0, 1024, phase=1)  # minimum phase not implemented
