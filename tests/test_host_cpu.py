@@ -1,0 +1,162 @@
+"""CPU tests of the product's host side: C-ABI surface, planner, filter design, scheduler.
+
+No compute call is made (there is no CPU fallback); everything here is the plan-level API.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+from port_oracle import PortOracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+VEC = np.load(os.path.join(G, "ref_vectors.npz"))
+NAMES = [str(n) for n in VEC["names"]]
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "r8bgpu.h")).read()
+    declared = set(re.findall(r"R8BGPU_API[^;(]*?\b(r8bgpu_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    L = ctypes.CDLL(pkg.lib_path())
+    for name in sorted(declared):
+        assert hasattr(L, name), "libr8bgpu.so does not export " + name
+    assert declared == set(pkg._SYMBOLS), declared ^ set(pkg._SYMBOLS)
+
+
+def test_cubin_is_sm100a(pkg):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", pkg.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_scheduler_matches_golden_counts(pkg, name):
+    p = VEC[name + "/params"]
+    lens = [int(v) for v in VEC[name + "/lens"]]
+    plan = pkg.Plan(p[0], p[1], max(lens), p[2], p[3], extfft=int(p[4]))
+    assert plan.simulate(lens) == [int(v) for v in VEC[name + "/counts"]]
+    assert plan.max_out_len == int(p[6])
+    assert plan.in_len_before_out_pos(0) == int(p[7])
+    assert plan.in_len_before_out_pos(1000) == int(p[8])
+
+
+RATES = [(44100.0, 96000.0), (48000.0, 44100.0), (48000.0, 47999.0), (192000.0, 44100.0), (44100.0, 88200.0),
+         (44100.0, 176400.0), (96000.0, 48000.0), (44100.0, 192000.0), (44100.0, 132300.0), (48000.0, 32000.0),
+         (32000.0, 48000.0), (48000.0, 36000.0), (2822400.0, 44100.0), (48000.0, 16000.0), (8000.0, 48000.0),
+         (44100.0, 22050.5), (1.0, 2.0), (44100.0, 44100.0), (11025.0, 96000.0), (96000.0, 11025.0)]
+
+
+@pytest.mark.parametrize("src,dst", RATES)
+def test_plan_equals_port_design(pkg, src, dst):
+    """Product planner/designer (C++) and the oracle port (C) are separate implementations of the
+    same reference formulas on the same libm: chains and filter data must agree bit for bit."""
+    plan = pkg.Plan(src, dst, 4096, 2.0, pkg.ATTEN_24)
+    r = PortOracle().Resampler(src, dst, 4096, 2.0, pkg.ATTEN_24)
+    st = plan.stages()
+    assert [s["kind"] for s in st] == r.stage_kinds()
+    assert plan.max_out_len == r.max_out_len
+    for i in range(len(st)):
+        assert np.array_equal(plan.stage_data(i), r.stage_data(i)), "stage %d data differs" % i
+    for pos in (0, 1, 999, 54321):
+        assert plan.in_len_before_out_pos(pos) == r.in_len_before_out_pos(pos)
+
+
+@pytest.mark.parametrize("src,dst", RATES)
+def test_scheduler_equals_reference(pkg, ref, src, dst):
+    rng = np.random.default_rng(int(src + dst))
+    lens = [4096, 4096] + [int(v) for v in rng.integers(0, 4097, 10)] + [0, 1, 4096]
+    plan = pkg.Plan(src, dst, 4096, 2.0, pkg.ATTEN_24)
+    r = ref.Resampler(src, dst, 4096, 2.0, pkg.ATTEN_24)
+    x = np.zeros(4096)
+    assert plan.simulate(lens) == [len(r.process(x[:l])) for l in lens]
+    assert plan.max_out_len == r.max_out_len
+    for n in (1, 10, 1000):
+        assert plan.input_required_for_output(n) == r.input_required_for_output(n)
+
+
+def test_in_len_before_out_start_matches_reference(pkg, ref):
+    for src, dst in [(44100.0, 96000.0), (48000.0, 44100.0), (192000.0, 44100.0)]:
+        plan = pkg.Plan(src, dst, 1024, 2.0, pkg.ATTEN_24)
+        r = ref.Resampler(src, dst, 1024, 2.0, pkg.ATTEN_24)
+        cs = np.cumsum(plan.simulate([1] * 8192))
+        mine = int(np.nonzero(cs > 0)[0][0])
+        assert mine == r.in_len_before_out_start(0)
+        # the two "instant" functions agree with the iterative one, as bench/zerotest.cpp:115-128 checks
+        assert plan.in_len_before_out_pos(0) == mine
+
+
+def test_lowpass_spectrum_matches_reference(pkg, ref):
+    for nf, tb, att, gain in [(0.5, 2.0, 180.15, 2.0), (0.459375, 2.0, 180.15, 2.0), (0.5, 0.5, 218.0, 2.0),
+                              (1 / 3, 30.0, 109.56, 3.0), (0.3, 5.0, 55.0, 1.0), (0.5, 45.0, 49.0, 1.0)]:
+        p = pkg.Plan.single_stage(0, [nf, tb, att, gain, 1, 1], 1024)
+        st = p.stages()[0]
+        h = p.stage_data(0)
+        r = ref.lpfilter(nf, tb, att, gain)
+        assert st["kernel_len"] == r["kernel_len"] and st["block_len_bits"] == r["block_len_bits"]
+        K = st["kernel_len"]
+        L = (K - 1) // 2
+        b2 = 2 << r["block_len_bits"]
+        z = np.zeros(b2)
+        z[:L + 1] = h[L:]
+        z[b2 - L:] = h[:L]
+        H = np.fft.rfft(z).real
+        assert np.max(np.abs(H - r["spectrum"])) <= 8 * ou.EPS * gain  # both sides carry FFT rounding
+
+
+def test_frac_banks_and_halfbands_bit_exact(pkg, ref):
+    for src, dst, att, third in [(88200.0, 96000.0, 180.15, 0), (96000.0, 44100.0, 180.15, 0),
+                                 (48000.0, 47999.0, 180.15, 0), (48000.0, 47999.0, 136.45, 0),
+                                 (48000.0, 47999.0, 109.56, 1), (88200.0, 96000.0, 206.91, 1)]:
+        ok, a, b = ref.whole_stepping(src, dst)
+        r = ref.fracbank(b if ok else -1, 1 if ok else 3, 2 if ok else 8, att, bool(third))
+        p = pkg.Plan.single_stage(1, [src, dst, att, third], 1024)
+        assert np.array_equal(p.stage_data(0).reshape(r["table"].shape), r["table"])
+    for third in (0, 1):
+        for steep in range(8):
+            for att in (50.0, 100.0, 136.45, 180.15, 206.91, 300.0):
+                t, a = ref.hbfilter(att, steep, bool(third))
+                p = pkg.Plan.single_stage(3, [att, steep, third], 1024)
+                assert np.array_equal(p.stage_data(0), t) and p.stages()[0]["atten"] == a
+
+
+def test_passthrough_and_errors(pkg):
+    assert pkg.Plan(48000.0, 48000.0, 256).passthrough
+    for bad in [dict(src_rate=0.0, dst_rate=1.0, max_in_len=16), dict(src_rate=1.0, dst_rate=2.0, max_in_len=0),
+                dict(src_rate=1.0, dst_rate=2.0, max_in_len=16, phase=1),
+                dict(src_rate=1.0, dst_rate=2.0, max_in_len=16, trans_band=0.1),
+                dict(src_rate=1.0, dst_rate=2.0, max_in_len=16, atten=300.0)]:
+        with pytest.raises(pkg.R8bGpuError):
+            pkg.Plan(**bad)
+    with pytest.raises(pkg.R8bGpuError):
+        pkg.Plan(44100.0, 96000.0, 64).simulate([65])  # l > MaxInLen
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device the batch API must fail loudly, never compute on the host."""
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(pkg.R8bGpuError):
+        pkg.Batch(pkg.Plan(44100.0, 96000.0, 64), 2)
+    with pytest.raises(pkg.R8bGpuError):
+        pkg.CDSPResampler24(44100.0, 96000.0, 64)
+
+
+def test_product_never_touches_oracle():
+    """The shipped sources must not reference oracle/ (only tests, smoke() and bench.py may)."""
+    pdir = os.path.join(ROOT, "r8brain-free-src_b200")
+    for base, _, files in os.walk(pdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc")):
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt.lower(), f
+    inc = open(os.path.join(ROOT, "include", "r8bgpu.h")).read()
+    assert "oracle" not in inc.lower()
