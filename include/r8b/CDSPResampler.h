@@ -1,0 +1,260 @@
+// include/r8b/CDSPResampler.h -- header-style C++ front-end in namespace r8b over the r8bgpu C-ABI.
+//
+// Drop-in for the reference's CDSPResampler.h on the process() path: same class names,
+// constructor arguments, method names and ownership rules (CDSPResampler.h:117-651,729-810 of
+// avaneev/r8brain-free-src); the per-channel CPU pipeline behind them is replaced by sm_100a
+// kernels reached through include/r8bgpu.h.  Link with -lr8bgpu.
+//
+//   r8b::CDSPResampler / CDSPResampler16 / CDSPResampler16IR / CDSPResampler24
+//        one stream per object, HOST buffers; process() = H2D + kernels + D2H per call.
+//        Meant for drop-in correctness; it cannot be fast (one PCIe round trip per call).
+//   r8b::CDSPResamplerBatch (new)
+//        N independent channels processed in lock-step -- the shape of example.cpp:30-67 --
+//        with host OR device planar buffers.  This is the intended production entry.
+//
+// Configuration macros (r8bconf.h surface).  The FFT back-end selectors R8B_IPP, R8B_PFFFT,
+// R8B_PFFFT_DOUBLE, R8B_FLOATFFT are accepted and ignored (there is no CPU FFT and no CPU
+// fallback).  R8B_EXTFFT and R8B_FASTTIMING change the plan exactly as they change the reference
+// (block length -> emission latency; interpolator timing) and are forwarded to the planner.
+// R8BASSERT / R8BCONSOLE keep their meaning (no-ops unless defined by the user).
+#ifndef R8B_CDSPRESAMPLER_B200_INCLUDED
+#define R8B_CDSPRESAMPLER_B200_INCLUDED
+
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../r8bgpu.h"
+
+#ifndef R8B_EXTFFT
+#define R8B_EXTFFT 0
+#endif
+#ifndef R8B_FASTTIMING
+#define R8B_FASTTIMING 0
+#endif
+#ifndef R8BASSERT
+#define R8BASSERT(e)
+#endif
+#ifndef R8BCONSOLE
+#define R8BCONSOLE(...)
+#endif
+
+namespace r8b {
+
+/// Filter phase response (CDSPFIRFilter.h:34-46).  Only fprLinearPhase is implemented.
+enum EDSPFilterPhaseResponse { fprLinearPhase = 0, fprMinPhase = 1 };
+
+/// N channels resampled in lock-step on one GPU.
+class CDSPResamplerBatch {
+public:
+    CDSPResamplerBatch(const int NumChannels, const double SrcSampleRate, const double DstSampleRate,
+                       const int aMaxInLen, const double ReqTransBand = 2.0, const double ReqAtten = 206.91,
+                       const EDSPFilterPhaseResponse ReqPhase = fprLinearPhase, const int Device = -1)
+        : Plan(r8bgpu_plan_create(SrcSampleRate, DstSampleRate, aMaxInLen, ReqTransBand, ReqAtten,
+                                  (int) ReqPhase, R8B_EXTFFT, R8B_FASTTIMING))
+        , Batch(NULL)
+        , Channels(NumChannels)
+        , Dev(Device)
+        , MaxInLen(aMaxInLen)
+    {
+        R8BASSERT(Plan != NULL);
+        if (Plan != NULL) {
+            char buf[1024];
+            r8bgpu_plan_describe(Plan, buf, (int) sizeof(buf));
+            R8BCONSOLE("%s", buf);
+            (void) buf;
+        }
+    }
+
+    ~CDSPResamplerBatch()
+    {
+        if (Batch != NULL) r8bgpu_batch_destroy(Batch);
+        if (Plan != NULL) r8bgpu_plan_destroy(Plan);
+    }
+
+    bool isValid() const { return Plan != NULL; }
+    const char* getLastError() const { return r8bgpu_last_error(); }
+    int getNumChannels() const { return Channels; }
+    int getMaxOutLen(const int /* MaxInLen */ = 0) const { return Plan ? r8bgpu_plan_max_out_len(Plan) : 0; }
+    int getInLenBeforeOutPos(const int ReqOutPos) const { return r8bgpu_plan_in_len_before_out_pos(Plan, ReqOutPos); }
+    int getInputRequiredForOutput(const int ReqOutSamples) const { return r8bgpu_plan_input_required_for_output(Plan, ReqOutSamples); }
+    int getLatency() const { return 0; }
+    double getLatencyFrac() const { return r8bgpu_plan_latency_frac(Plan); }
+
+    void clear()
+    {
+        if (Batch != NULL) r8bgpu_batch_clear(Batch);
+    }
+
+    /// Host planar buffers: channel c at ip + c*InStride / op + c*OutStride (strides in doubles).
+    /// Returns samples written per channel (same for all channels), or -1.
+    int process(const double* ip, const size_t InStride, const int l, double* op, const size_t OutStride,
+                const int OutCap)
+    {
+        if (!ensure()) return -1;
+        return r8bgpu_batch_process_host(Batch, ip, InStride, l, op, OutStride, OutCap);
+    }
+
+    /// Device planar buffers; asynchronous on the batch stream (see r8bgpu_batch_set_stream()).
+    int processDevice(const double* d_ip, const size_t InStride, const int l, double* d_op, const size_t OutStride,
+                      const int OutCap)
+    {
+        if (!ensure()) return -1;
+        return r8bgpu_batch_process(Batch, d_ip, InStride, l, d_op, OutStride, OutCap);
+    }
+
+    void setStream(void* CudaStream)
+    {
+        if (ensure()) r8bgpu_batch_set_stream(Batch, CudaStream);
+    }
+
+    void sync()
+    {
+        if (Batch != NULL) r8bgpu_batch_sync(Batch);
+    }
+
+    r8bgpu_batch* handle()
+    {
+        ensure();
+        return Batch;
+    }
+
+private:
+    r8bgpu_plan* Plan;
+    r8bgpu_batch* Batch;
+    int Channels;
+    int Dev;
+    int MaxInLen;
+
+    bool ensure()
+    {
+        if (Batch == NULL && Plan != NULL) Batch = r8bgpu_batch_create(Plan, Channels, Dev);
+        R8BASSERT(Batch != NULL);
+        return Batch != NULL;
+    }
+
+    CDSPResamplerBatch(const CDSPResamplerBatch&);
+    CDSPResamplerBatch& operator=(const CDSPResamplerBatch&);
+};
+
+/// Single-stream object with the reference's exact call shape.
+class CDSPResampler {
+public:
+    CDSPResampler(const double SrcSampleRate, const double DstSampleRate, const int aMaxInLen,
+                  const double ReqTransBand = 2.0, const double ReqAtten = 206.91,
+                  const EDSPFilterPhaseResponse ReqPhase = fprLinearPhase)
+        : Impl(1, SrcSampleRate, DstSampleRate, aMaxInLen, ReqTransBand, ReqAtten, ReqPhase)
+        , MaxInLen(aMaxInLen)
+        , IsSame(SrcSampleRate == DstSampleRate)
+    {
+        R8BASSERT(SrcSampleRate > 0.0);
+        R8BASSERT(DstSampleRate > 0.0);
+        R8BASSERT(aMaxInLen > 0);
+        OutBuf.resize((size_t) (Impl.getMaxOutLen() > 0 ? Impl.getMaxOutLen() : 1));
+    }
+
+    virtual ~CDSPResampler() {}
+
+    virtual int getInLenBeforeOutPos(const int ReqOutPos) const { return Impl.getInLenBeforeOutPos(ReqOutPos); }
+    int getInputRequiredForOutput(const int ReqOutSamples) const { return Impl.getInputRequiredForOutput(ReqOutSamples); }
+    virtual int getLatency() const { return 0; }
+    virtual double getLatencyFrac() const { return Impl.getLatencyFrac(); }
+    virtual int getMaxOutLen(const int /* MaxInLen */) const { return Impl.getMaxOutLen(); }
+    virtual void clear() { Impl.clear(); }
+
+    /// As CDSPResampler.h:443-464: feeds single samples until the output passes ReqOutPos.
+    int getInLenBeforeOutStart(const int ReqOutPos = 0)
+    {
+        int inc = 0, outc = 0;
+        while (true) {
+            double ins = 0.0;
+            double* op;
+            outc += process(&ins, 1, op);
+            if (outc > ReqOutPos) {
+                clear();
+                return inc;
+            }
+            inc++;
+        }
+    }
+
+    /// As CDSPResampler.h:559-575: `op0` receives a pointer to an internal buffer that stays valid
+    /// until the next call; the input is never written; equal rates hand the input back.
+    virtual int process(double* ip0, int l, double*& op0)
+    {
+        R8BASSERT(l >= 0);
+        if (IsSame) {
+            op0 = ip0;
+            return l;
+        }
+        op0 = &OutBuf[0];
+        const int n = Impl.process(ip0, (size_t) l, l, op0, OutBuf.size(), (int) OutBuf.size());
+        R8BASSERT(n >= 0);
+        return n < 0 ? 0 : n;
+    }
+
+    /// As CDSPResampler.h:592-651.
+    template <typename Tin, typename Tout>
+    void oneshot(const Tin* ip, int iplen, Tout* op, int oplen)
+    {
+        std::vector<double> Buf((size_t) MaxInLen);
+        bool IsZero = false;
+        while (oplen > 0) {
+            int rc;
+            double* p;
+            if (iplen == 0) {
+                rc = MaxInLen;
+                p = &Buf[0];
+                if (!IsZero) {
+                    IsZero = true;
+                    memset(p, 0, (size_t) MaxInLen * sizeof(double));
+                }
+            } else {
+                rc = iplen < MaxInLen ? iplen : MaxInLen;
+                p = &Buf[0];
+                for (int i = 0; i < rc; i++) p[i] = (double) ip[i];
+                ip += rc;
+                iplen -= rc;
+            }
+            double* op0;
+            int wc = process(p, rc, op0);
+            if (wc > oplen) wc = oplen;
+            for (int i = 0; i < wc; i++) op[i] = (Tout) op0[i];
+            op += wc;
+            oplen -= wc;
+        }
+        clear();
+    }
+
+private:
+    CDSPResamplerBatch Impl;
+    std::vector<double> OutBuf;
+    int MaxInLen;
+    bool IsSame;
+};
+
+class CDSPResampler16 : public CDSPResampler {
+public:
+    CDSPResampler16(const double SrcSampleRate, const double DstSampleRate, const int aMaxInLen,
+                    const double ReqTransBand = 2.0)
+        : CDSPResampler(SrcSampleRate, DstSampleRate, aMaxInLen, ReqTransBand, 136.45, fprLinearPhase) {}
+};
+
+class CDSPResampler16IR : public CDSPResampler {
+public:
+    CDSPResampler16IR(const double SrcSampleRate, const double DstSampleRate, const int aMaxInLen,
+                      const double ReqTransBand = 2.0)
+        : CDSPResampler(SrcSampleRate, DstSampleRate, aMaxInLen, ReqTransBand, 109.56, fprLinearPhase) {}
+};
+
+class CDSPResampler24 : public CDSPResampler {
+public:
+    CDSPResampler24(const double SrcSampleRate, const double DstSampleRate, const int aMaxInLen,
+                    const double ReqTransBand = 2.0)
+        : CDSPResampler(SrcSampleRate, DstSampleRate, aMaxInLen, ReqTransBand, 180.15, fprLinearPhase) {}
+};
+
+} // namespace r8b
+
+#endif // R8B_CDSPRESAMPLER_B200_INCLUDED

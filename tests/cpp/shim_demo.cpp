@@ -1,0 +1,47 @@
+// tests/cpp/shim_demo.cpp -- uses include/r8b/CDSPResampler.h exactly the way example.cpp:30-67 uses the
+// reference header: one CDSPResampler24 per channel, the same block length for every channel.
+//   shim_demo <in.f64> <out.f64> <n_ch> <frames> <src> <dst> <block>      (planar raw doubles)
+// Without a GPU, "shim_demo --plan <src> <dst> <block>" prints only plan-level getters.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "r8b/CDSPResampler.h"
+
+int main(int argc, char** argv)
+{
+    if (argc == 5 && strcmp(argv[1], "--plan") == 0) {
+        r8b::CDSPResampler24 rs(atof(argv[2]), atof(argv[3]), atoi(argv[4]));
+        printf("%d %d %d %g\n", rs.getMaxOutLen(0), rs.getInLenBeforeOutPos(0), rs.getInputRequiredForOutput(1000),
+               rs.getLatencyFrac());
+        return 0;
+    }
+    if (argc != 8) return 2;
+    const int n_ch = atoi(argv[3]), frames = atoi(argv[4]), block = atoi(argv[7]);
+    const double src = atof(argv[5]), dst = atof(argv[6]);
+    std::vector<double> in((size_t) n_ch * frames);
+    FILE* f = fopen(argv[1], "rb");
+    if (!f || fread(in.data(), sizeof(double), in.size(), f) != in.size()) return 3;
+    fclose(f);
+    std::vector<r8b::CDSPResampler24*> rs;
+    for (int c = 0; c < n_ch; c++) rs.push_back(new r8b::CDSPResampler24(src, dst, block));
+    std::vector<std::vector<double> > out((size_t) n_ch);
+    for (int pos = 0; pos < frames; pos += block) {
+        const int l = frames - pos < block ? frames - pos : block;
+        for (int c = 0; c < n_ch; c++) {
+            double* op;
+            const int n = rs[(size_t) c]->process(&in[(size_t) c * frames + pos], l, op);
+            out[(size_t) c].insert(out[(size_t) c].end(), op, op + n);
+        }
+    }
+    f = fopen(argv[2], "wb");
+    for (int c = 0; c < n_ch; c++) {
+        const long long n = (long long) out[(size_t) c].size();
+        fwrite(&n, sizeof n, 1, f);
+        fwrite(out[(size_t) c].data(), sizeof(double), (size_t) n, f);
+        delete rs[(size_t) c];
+    }
+    fclose(f);
+    return 0;
+}

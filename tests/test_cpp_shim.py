@@ -1,0 +1,56 @@
+"""The header-style r8b:: front-end (include/r8b/CDSPResampler.h) compiled against libr8bgpu.so."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "shim_demo")
+
+
+def build_demo(pkg):
+    src = os.path.join(ROOT, "tests", "cpp", "shim_demo.cpp")
+    lib_dir = os.path.dirname(pkg.lib_path())
+    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(pkg.lib_path())):
+        return EXE
+    gxx = shutil.which("g++")
+    if gxx is None:
+        if os.path.exists(EXE):
+            return EXE
+        pytest.skip("no g++ and no prebuilt demo")
+    subprocess.run([gxx, "-O1", "-std=c++11", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
+                    "-L", lib_dir, "-lr8bgpu", "-Wl,-rpath," + lib_dir], check=True)
+    return EXE
+
+
+def test_shim_compiles_and_plans(pkg, ref):
+    exe = build_demo(pkg)
+    out = subprocess.run([exe, "--plan", "44100", "96000", "65536"], capture_output=True, text=True, check=True).stdout.split()
+    r = ref.Resampler(44100.0, 96000.0, 65536, 2.0, 180.15)
+    assert [int(out[0]), int(out[1]), int(out[2])] == [r.max_out_len, r.in_len_before_out_pos(0),
+                                                       r.input_required_for_output(1000)]
+
+
+@pytest.mark.gpu
+def test_shim_process_matches_reference(pkg, ref, tmp_path):
+    exe = build_demo(pkg)
+    n_ch, frames, block = 2, 20000, 4096
+    x = ou.white_noise(n_ch, frames, 31)
+    fin, fout = str(tmp_path / "in.f64"), str(tmp_path / "out.f64")
+    x.tofile(fin)
+    subprocess.run([exe, fin, fout, str(n_ch), str(frames), "44100", "96000", str(block)], check=True)
+    raw = open(fout, "rb").read()
+    pos = 0
+    for c in range(n_ch):
+        n = int(np.frombuffer(raw[pos:pos + 8], dtype=np.int64)[0])
+        y = np.frombuffer(raw[pos + 8:pos + 8 + 8 * n], dtype=np.float64)
+        pos += 8 + 8 * n
+        r = ref.Resampler(44100.0, 96000.0, block, 2.0, 180.15)
+        yr = np.concatenate([r.process(x[c, i:i + block]) for i in range(0, frames, block)])
+        assert len(yr) == n
+        m, rr = ou.parity_metrics(y, yr)
+        assert m <= 32 * ou.EPS and rr <= 4 * ou.EPS
