@@ -156,6 +156,12 @@ struct StageDev {
     // source ring of this stage (for stage 0: the input history ring)
     double* ring = nullptr;
     long long ring_cap = 0;
+    // fusion: a 2x BLOCKCONV immediately followed by a FRAC stage runs as ONE kernel
+    bool fused_with_next = false; // on the BLOCKCONV stage
+    bool fused_into_prev = false; // on the FRAC stage (its source ring is never materialised)
+    int* phase_off = nullptr;
+    int* phase_row = nullptr;
+    int yl = 0, yr = 0, ysh = 31, span_max = 0, bank_in_smem = 0;
 };
 
 } // namespace
@@ -196,6 +202,8 @@ struct r8bgpu_batch {
             cudaFree(d.tw);
             cudaFree(d.bank);
             cudaFree(d.ring);
+            cudaFree(d.phase_off);
+            cudaFree(d.phase_row);
         }
         cudaFree(st_in);
         cudaFree(st_out);
@@ -371,10 +379,42 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
         const StageDesc& s = st[i];
         StageDev& d = b->dev[i];
         const long long emit_in = (i == 0) ? 0 : st[i - 1].max_out_len;
-        d.ring_cap = next_pow2((long long) s.src_history + emit_in + 64);
-        const size_t ring_bytes = (size_t) d.ring_cap * (size_t) n_channels * sizeof(double);
-        if (!cuda_ok(cudaMalloc(&d.ring, ring_bytes), "batch_create: cudaMalloc(ring)")) return nullptr;
-        b->dev_bytes += ring_bytes;
+        // Fusable pair: [BlockConv 2/1 with a kernel that fits M=4096 tiles] -> [FracInterp].
+        if (s.kind == ST_BLOCKCONV && s.up == 2 && s.down == 1 && !s.block_exact && i + 1 < st.size() &&
+            (st[i + 1].kind == ST_FRAC_WHOLE || st[i + 1].kind == ST_FRAC_POLY) && !getenv("R8BGPU_NO_FUSION")) {
+            const StageDesc& f = st[i + 1];
+            const int lg = (s.lp.half_len + 1) / 2;
+            const int flen = f.bank.filter_len, fll = flen / 2 - 1;
+            int dmax = 0;
+            if (f.kind == ST_FRAC_WHOLE)
+                dmax = (int) (((long long) 7 * f.in_step + f.out_step - 1) / f.out_step) + 1;
+            const int yl = (fll + 2) & ~1;
+            const int yr = (dmax + flen - yl + 2 + 1) & ~1;
+            const int smax = fused_max_span(lg, yl, yr) & ~1;
+            if (smax >= 1024 && (f.kind == ST_FRAC_POLY || f.in_step < smax / 2)) {
+                d.fused_with_next = true;
+                b->dev[i + 1].fused_into_prev = true;
+                d.yl = yl;
+                d.yr = yr;
+                d.span_max = smax;
+                d.ysh = 31;
+                if (f.kind == ST_FRAC_WHOLE && (f.in_step & 1) == 0) {
+                    // lanes step by in_step doubles through the tile: make the padded stride odd
+                    int sh = 0;
+                    while (((f.in_step >> sh) & 1) == 0) sh++;
+                    d.ysh = sh < 4 ? 4 : sh;
+                    if (((f.in_step + (f.in_step >> d.ysh)) & 1) == 0) d.ysh = 31; // cannot fix; accept conflicts
+                }
+            }
+        }
+        if (d.fused_into_prev) {
+            d.ring_cap = 0; // the link stream lives only in shared memory
+        } else {
+            d.ring_cap = next_pow2((long long) s.src_history + emit_in + 64);
+            const size_t ring_bytes = (size_t) d.ring_cap * (size_t) n_channels * sizeof(double);
+            if (!cuda_ok(cudaMalloc(&d.ring, ring_bytes), "batch_create: cudaMalloc(ring)")) return nullptr;
+            b->dev_bytes += ring_bytes;
+        }
         if (s.kind == ST_BLOCKCONV) {
             if (s.up > 2) {
                 set_err("batch_create: BlockConvolver up-factor 3 is not implemented yet");
@@ -387,6 +427,7 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 d.fft_log2 = s.lp.block_len_bits + 1;
                 if (d.fft_log2 < 10 || d.fft_log2 > 12) d.fft_log2 = -1;
             }
+            if (d.fused_with_next) d.fft_log2 = 12; // the fused kernel is built for M = 4096
             if (d.fft_log2 < 0) {
                 set_err("batch_create: low-pass kernel too long for the in-shared-memory FFT tiles");
                 return nullptr;
@@ -404,6 +445,21 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
             if (!cuda_ok(cudaMalloc(&d.bank, nb), "cudaMalloc(bank)")) return nullptr;
             if (!cuda_ok(cudaMemcpy(d.bank, s.bank.table.data(), nb, cudaMemcpyHostToDevice), "copy bank")) return nullptr;
             b->dev_bytes += nb;
+            if (s.kind == ST_FRAC_WHOLE) {
+                // per output phase r: floor(r*InStep/OutStep) and the bank row (r*InStep) % OutStep
+                std::vector<int> off((size_t) s.out_step), row((size_t) s.out_step);
+                for (int r = 0; r < s.out_step; r++) {
+                    const long long pos = (long long) r * s.in_step;
+                    off[(size_t) r] = (int) (pos / s.out_step);
+                    row[(size_t) r] = (int) (pos % s.out_step);
+                }
+                const size_t tb = off.size() * sizeof(int);
+                if (!cuda_ok(cudaMalloc(&d.phase_off, tb), "cudaMalloc(phase)")) return nullptr;
+                if (!cuda_ok(cudaMalloc(&d.phase_row, tb), "cudaMalloc(phase)")) return nullptr;
+                cudaMemcpy(d.phase_off, off.data(), tb, cudaMemcpyHostToDevice);
+                cudaMemcpy(d.phase_row, row.data(), tb, cudaMemcpyHostToDevice);
+                d.bank_in_smem = (fused_smem_bytes((int) s.bank.table.size()) <= 220 * 1024) ? 1 : 0;
+            }
         }
     }
     r8bgpu_batch* raw = b.release();
@@ -468,6 +524,7 @@ int r8bgpu_batch_clear(r8bgpu_batch* b)
     DeviceGuard g(b->device);
     b->sched.clear();
     for (auto& d : b->dev) {
+        if (d.ring == nullptr) continue;
         if (!cuda_ok(cudaMemsetAsync(d.ring, 0, (size_t) d.ring_cap * (size_t) b->n_ch * sizeof(double), b->stream),
                      "batch_clear: cudaMemsetAsync"))
             return -1;
@@ -521,7 +578,9 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
         const StageDesc& s = P.stages[i];
         const StageCall& c = b->calls[i];
         const StageDev& d = b->dev[i];
-        if (c.e1 <= c.e0) continue;
+        if (d.fused_into_prev) continue; // handled together with the previous stage
+        const bool fused = d.fused_with_next;
+        if ((fused ? b->calls[i + 1].e1 <= b->calls[i + 1].e0 : c.e1 <= c.e0)) continue;
         SrcView src;
         src.ring = d.ring;
         src.ring_stride = d.ring_cap;
@@ -537,15 +596,16 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
         }
         src.avail = c.n1;
         DstView dst;
-        if (i + 1 == ns) {
+        const size_t last = fused ? i + 1 : i; // stage whose output this launch produces
+        if (last + 1 == ns) {
             dst.ptr = d_out;
             dst.stride = (long long) out_stride;
             dst.mask = -1;
-            dst.base = c.e0;
+            dst.base = b->calls[last].e0;
         } else {
-            dst.ptr = b->dev[i + 1].ring;
-            dst.stride = b->dev[i + 1].ring_cap;
-            dst.mask = b->dev[i + 1].ring_cap - 1;
+            dst.ptr = b->dev[last + 1].ring;
+            dst.stride = b->dev[last + 1].ring_cap;
+            dst.mask = b->dev[last + 1].ring_cap - 1;
             dst.base = 0;
         }
         r8bgpu_batch::EvPair ev{(int) i, nullptr, nullptr};
@@ -554,6 +614,53 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
             cudaEventCreate(&ev.b);
             cudaEventRecord(ev.a, st);
         }
+        if (fused) {
+            const StageDesc& f = P.stages[i + 1];
+            const StageCall& fc = b->calls[i + 1];
+            const StageDev& fd = b->dev[i + 1];
+            FusedParams p;
+            memset(&p, 0, sizeof p);
+            p.mode = f.kind == ST_FRAC_WHOLE ? 0 : 1;
+            p.flen = f.bank.filter_len;
+            p.fll = p.flen / 2 - 1;
+            p.e0 = fc.e0;
+            p.e1 = fc.e1;
+            if (p.mode == 0) {
+                p.p_lo = (fc.e0 * f.in_step) / f.out_step;
+                p.p_hi = ((fc.e1 - 1) * f.in_step) / f.out_step + 1;
+            } else {
+                p.p_lo = fc.p0;
+                p.p_hi = fc.p_last + 1;
+            }
+            p.p_lo &= ~1LL; // even (positions are >= 0)
+            const long long range = p.p_hi - p.p_lo;
+            long long nt = (range + d.span_max - 1) / d.span_max;
+            if (nt > 1 && (nt & 1)) nt++;
+            p.n_tiles = (int) nt;
+            p.span = (int) (((range + nt - 1) / nt + 1) & ~1LL);
+            p.yl = d.yl;
+            p.lg = d.lg;
+            p.ysh = d.ysh;
+            p.spec = d.spec;
+            p.tw = d.tw;
+            p.bank = fd.bank;
+            p.bank_len = (int) f.bank.table.size();
+            p.bank_in_smem = fd.bank_in_smem;
+            p.in_step = f.in_step;
+            p.out_step = f.out_step;
+            p.phase_off = fd.phase_off;
+            p.phase_row = fd.phase_row;
+            p.fracs = f.bank.fracs;
+            p.ssr = f.src_rate;
+            p.dsr = f.dst_rate;
+            p.in_counter0 = fc.in_counter0;
+            p.in_pos_int0 = fc.in_pos_int0;
+            p.in_pos_shift = fc.in_pos_shift;
+            p.fpos0 = fc.fpos0;
+            p.p0 = fc.p0;
+            launch_up2_frac(p, src, dst, b->n_ch, st);
+            b->launches++;
+        } else
         switch (s.kind) {
         case ST_BLOCKCONV: {
             BlockConvParams p;

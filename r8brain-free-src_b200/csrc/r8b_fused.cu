@@ -1,0 +1,364 @@
+// r8b_fused.cu -- fused "2x BlockConvolver -> FracInterpolator" kernel: the 2x-rate stream never
+// touches HBM.  This is the whole CDSPResampler::process() chain of BASELINE configs 1/2/3/5
+// (CDSPResampler.h:218-333 case "upsampling or fractional downsampling down to 2X",
+// CDSPBlockConvolver.h:252-354 + CDSPFracInterpolator.h:861-1179) in ONE launch per call.
+//
+// One CTA (512 threads) = one channel x one PAIR of consecutive tiles (a,b):
+//   A. gather x_a + i*x_b straight from global into registers, first DIF pass   (threads 0..255)
+//   B. DIF passes 2,3                                                             (threads 0..255)
+//   C. per frequency pair (k, M-k): split the packed spectrum, multiply by G, write Y_a -> bufB and
+//      Y_b -> bufA in place                                                      (all threads)
+//   D. both inverse transforms side by side (thread>>8 selects the buffer); the last pass stores
+//      the 2x-rate samples y[2m], y[2m+1] as plain doubles in an interpolation-friendly layout
+//   E. fractional-delay interpolation from shared memory, results written to global:
+//        whole stepping : register tile of R=8 output phases x Q=3 stepping cycles per lane;
+//                         lanes = different cycles (distinct y addresses, conflict-free by
+//                         construction of the layout), phase = warp-uniform (bank rows broadcast)
+//        order-2 bank   : one output per thread, exact reference timing arithmetic
+// Tiles own disjoint ranges of the 2x-rate position p; each tile's valid y range overlaps its
+// neighbours by one interpolation window so no state is exchanged between CTAs.
+#include "r8b_kernels.h"
+
+#include <climits>
+
+#include "r8b_fft.cuh"
+
+namespace r8bgpu {
+
+namespace {
+
+__device__ __forceinline__ double src_read_f(const SrcView& v, int ch, long long n)
+{
+    if (n >= v.avail) return 0.0;
+    if (n >= v.cur_base) return __ldg(v.cur + (long long) ch * v.cur_stride + (n - v.cur_base));
+    return __ldg(v.ring + (long long) ch * v.ring_stride + (n & v.ring_mask));
+}
+
+__device__ __forceinline__ void dst_write_f(const DstView& v, int ch, long long idx, double x)
+{
+    v.ptr[(long long) ch * v.stride + ((idx - v.base) & v.mask)] = x;
+}
+
+constexpr int FM = 4096;            // FFT length of the fused kernel
+constexpr int FNT = 512;            // threads per CTA
+constexpr int FPL = fft_padded_len(FM);
+constexpr int IR = 8;               // interpolation register tile: phases per lane
+constexpr int IQ = 3;               // ... x stepping cycles per lane
+
+__device__ __forceinline__ int ylay(int i, int ysh) { return i + (i >> ysh); }
+
+// forward pass 1 fused with the gather from global memory (radix 16, NCUR = M, D = 256)
+__device__ __forceinline__ void fwd_pass1_gather(double2* __restrict__ s, const double2* __restrict__ tw,
+                                                 const SrcView& src, int ch, long long wa, long long wb,
+                                                 bool has_b, int r)
+{
+    double2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int n = r + 256 * j;
+        v[j].x = src_read_f(src, ch, wa + n);
+        v[j].y = has_b ? src_read_f(src, ch, wb + n) : 0.0;
+    }
+    Network<16, +1>::run(v);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        double2 x = v[bitrev<16>(q)];
+        if (q > 0) x = cmul<+1>(x, __ldg(&tw[r * q]));
+        s[fft_pad(r + q * 256)] = x;
+    }
+}
+
+template <int NCUR>
+__device__ __forceinline__ void fwd_pass(double2* __restrict__ s, const double2* __restrict__ tw_g,
+                                         const double2* __restrict__ tw2_s, int g)
+{
+    constexpr int D = NCUR / 16;
+    const int blk = g / D, r = g % D;
+    const int base = blk * NCUR + r;
+    double2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = s[fft_pad(base + j * D)];
+    Network<16, +1>::run(v);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        double2 x = v[bitrev<16>(q)];
+        if (D > 1 && q > 0) x = cmul<+1>(x, tw2_s[r * q]); // NCUR == 256: W_256^(r q) from shared memory
+        s[fft_pad(base + q * D)] = x;
+    }
+    (void) tw_g;
+}
+
+template <int NCUR>
+__device__ __forceinline__ void inv_pass(double2* __restrict__ s, const double2* __restrict__ tw2_s, int g)
+{
+    constexpr int D = NCUR / 16;
+    const int blk = g / D, r = g % D;
+    const int base = blk * NCUR + r;
+    double2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        double2 x = s[fft_pad(base + q * D)];
+        if (D > 1 && q > 0) x = cmul<-1>(x, tw2_s[r * q]);
+        v[q] = x;
+    }
+    Network<16, -1>::run(v);
+#pragma unroll
+    for (int j = 0; j < 16; j++) s[fft_pad(base + j * D)] = v[bitrev<16>(j)];
+}
+
+} // namespace
+
+// MODE 0: whole stepping, MODE 1: order-2 polynomial bank.
+template <int MODE>
+__global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src, DstView dst)
+{
+    extern __shared__ double2 smem[];
+    double2* bufA = smem;              // forward spectrum Z, later Y_b / y_b
+    double2* bufB = smem + FPL;        // Y_a / y_a
+    double2* tw2 = smem + 2 * FPL;     // W_256^k, k < 256
+    double* sbank = reinterpret_cast<double*>(tw2 + 256); // whole-step bank (if it fits)
+    __shared__ int s_j[2];
+
+    const int tid = threadIdx.x;
+    const int n_pairs = (p.n_tiles + 1) >> 1;
+    const int ch = blockIdx.x / n_pairs;
+    const int pair = blockIdx.x - ch * n_pairs;
+    const int ta = 2 * pair;
+    const bool has_b = (ta + 1) < p.n_tiles;
+    // owned 2x-rate position ranges [A0,A1) and [B0,B1)
+    const long long A0 = p.p_lo + (long long) ta * p.span;
+    long long A1 = A0 + p.span;
+    if (A1 > p.p_hi) A1 = p.p_hi;
+    const long long B0 = A1;
+    long long B1 = has_b ? B0 + p.span : B0;
+    if (B1 > p.p_hi) B1 = p.p_hi;
+    // valid y of tile t starts at own_start - YL (even) = 2 * (first valid m); window starts lg earlier
+    const long long wa = (A0 - p.yl) / 2 - p.lg;
+    const long long wb = (B0 - p.yl) / 2 - p.lg;
+
+    // tables into shared memory
+    for (int i = tid; i < 256; i += FNT) tw2[i] = __ldg(&p.tw[i * (FM / 256)]);
+    if (MODE == 0 && p.bank_in_smem)
+        for (int i = tid; i < p.bank_len; i += FNT) sbank[i] = __ldg(&p.bank[i]);
+
+    if (tid < 256) fwd_pass1_gather(bufA, p.tw, src, ch, wa, wb, has_b, tid);
+    __syncthreads();
+    if (tid < 256) fwd_pass<256>(bufA, p.tw, tw2, tid);
+    __syncthreads();
+    if (tid < 256) fwd_pass<16>(bufA, p.tw, tw2, tid);
+    __syncthreads();
+
+    // C. frequency pairs
+    for (int s1 = tid; s1 < FM; s1 += FNT) {
+        const int k = freq_of<FM>(s1);
+        if (k > FM / 2) continue;
+        const int k2 = (FM - k) & (FM - 1);
+        const int s2 = slot_of<FM>(k2);
+        const double2 z1 = bufA[fft_pad(s1)];
+        const double2 z2 = bufA[fft_pad(s2)];
+        const double2 g1 = __ldg(&p.spec[s1]);
+        const double2 g2 = __ldg(&p.spec[s2]);
+        // X_a[k] = z1 + conj z2 (the 1/2 lives in G); X_a[M-k] = conj X_a[k]
+        const double2 xa = make_double2(z1.x + z2.x, z1.y - z2.y);
+        const double2 xb = make_double2(z1.y + z2.y, z2.x - z1.x); // -i (z1 - conj z2)
+        bufB[fft_pad(s1)] = cmul<+1>(xa, g1);
+        bufA[fft_pad(s1)] = cmul<+1>(xb, g1);
+        if (s2 != s1) {
+            bufB[fft_pad(s2)] = cmul<+1>(make_double2(xa.x, -xa.y), g2);
+            bufA[fft_pad(s2)] = cmul<+1>(make_double2(xb.x, -xb.y), g2);
+        }
+    }
+    __syncthreads();
+
+    // D. two inverse transforms side by side
+    {
+        double2* buf = (tid < 256) ? bufB : bufA;
+        const int g = tid & 255;
+        inv_pass<16>(buf, tw2, g);
+        __syncthreads();
+        inv_pass<256>(buf, tw2, g);
+        __syncthreads();
+        // last pass: NCUR = M, D = 256, twiddle W_M^(r q) conj; results leave in y layout
+        double2 v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            double2 x = buf[fft_pad(g + q * 256)];
+            if (q > 0) x = cmul<-1>(x, __ldg(&p.tw[g * q]));
+            v[q] = x;
+        }
+        Network<16, -1>::run(v);
+        __syncthreads();
+        double* yb = reinterpret_cast<double*>(buf);
+        const long long w = (tid < 256) ? wa : wb;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int e = g + j * 256;           // local input-rate position
+            double2 x = v[bitrev<16>(j)];
+            const long long t0 = 2 * (w + e);    // absolute 2x-rate index of x.x
+            if (t0 < 0) x = make_double2(0.0, 0.0); // the reference's interpolator starts from silence
+            yb[ylay(2 * e, p.ysh)] = x.x;
+            yb[ylay(2 * e + 1, p.ysh)] = x.y;
+        }
+    }
+    __syncthreads();
+
+    const double* ya = reinterpret_cast<const double*>(bufB);
+    const double* ybuf_b = reinterpret_cast<const double*>(bufA);
+    const long long ya0 = 2 * wa, yb0 = 2 * wb;   // absolute 2x index of local double 0
+    const long long bsel = has_b ? B0 - p.yl : LLONG_MAX; // windows starting at or after this use tile b
+    constexpr int YMAX = 2 * FM;                  // doubles per tile buffer (before layout padding)
+
+    if (MODE == 0) {
+        // outputs j with A0 <= floor(j*InStep/OutStep) < B1, clipped to [e0,e1)
+        long long ja = (A0 * p.out_step + p.in_step - 1) / p.in_step;
+        long long jb = (B1 * p.out_step + p.in_step - 1) / p.in_step;
+        if (ja < p.e0) ja = p.e0;
+        if (jb > p.e1) jb = p.e1;
+        if (jb <= ja) return;
+        const long long c_first = ja / p.out_step, c_last = (jb - 1) / p.out_step;
+        const int warp = tid >> 5, lane = tid & 31;
+        const int n_groups = (p.out_step + IR - 1) / IR;
+        const int n_chunks = (int) ((c_last - c_first + 32 * IQ) / (32 * IQ));
+        const int n_tasks = n_groups * n_chunks;
+        const double* bank = p.bank_in_smem ? sbank : p.bank;
+        for (int task = warp; task < n_tasks; task += FNT / 32) {
+            const int grp = task % n_groups, chunk = task / n_groups;
+            const int r0 = grp * IR;
+            int d[IR], row[IR];
+            const int o0 = __ldg(&p.phase_off[r0]);
+#pragma unroll
+            for (int r = 0; r < IR; r++) {
+                const int rr = (r0 + r < p.out_step) ? r0 + r : p.out_step - 1;
+                d[r] = __ldg(&p.phase_off[rr]) - o0;
+                row[r] = __ldg(&p.phase_row[rr]) * p.flen;
+            }
+            const int smax = d[IR - 1] + p.flen;
+            const double* yp[IQ];
+            long long cq[IQ];
+            int yi[IQ];
+#pragma unroll
+            for (int q = 0; q < IQ; q++) {
+                cq[q] = c_first + (long long) chunk * (32 * IQ) + q * 32 + lane;
+                long long c = cq[q] <= c_last ? cq[q] : c_last;
+                const long long ws = c * p.in_step + o0 - p.fll; // first y index of the tile window
+                const bool use_b = ws >= bsel;
+                yp[q] = use_b ? ybuf_b : ya;
+                long long li = ws - (use_b ? yb0 : ya0);
+                // phases of the edge cycles that this pair does not own may point outside the tile;
+                // their results are never stored, keep the reads inside the buffer
+                if (li < 0) li = 0;
+                if (li > YMAX - smax) li = YMAX - smax;
+                yi[q] = (int) li;
+            }
+            double acc[IR][IQ];
+#pragma unroll
+            for (int r = 0; r < IR; r++)
+#pragma unroll
+                for (int q = 0; q < IQ; q++) acc[r][q] = 0.0;
+#pragma unroll 1
+            for (int s = 0; s < smax; s++) {
+                double yv[IQ];
+#pragma unroll
+                for (int q = 0; q < IQ; q++) yv[q] = yp[q][ylay(yi[q] + s, p.ysh)];
+#pragma unroll
+                for (int r = 0; r < IR; r++) {
+                    const int i = s - d[r];
+                    if ((unsigned) i < (unsigned) p.flen) {
+                        const double b = bank[row[r] + i];
+#pragma unroll
+                        for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < IQ; q++) {
+                if (cq[q] > c_last) continue;
+                const long long j0 = cq[q] * p.out_step + r0;
+#pragma unroll
+                for (int r = 0; r < IR; r++) {
+                    const long long j = j0 + r;
+                    if (r0 + r < p.out_step && j >= ja && j < jb) dst_write_f(dst, ch, j, acc[r][q]);
+                }
+            }
+        }
+    } else {
+        // order-2 bank: output k of this call (k >= 0) sits at (p_k, fpos_k); find the pair's k range
+        if (tid == 0) {
+            // p_k is non-decreasing in k: binary search the first k with p_k >= A0 and with p_k >= B1
+            long long lim[2] = {A0, B1};
+            const long long nk = p.e1 - p.e0;
+            for (int t = 0; t < 2; t++) {
+                long long lo = 0, hi = nk; // answer in [0, nk]
+                while (lo < hi) {
+                    const long long mid = lo + (hi - lo) / 2;
+                    long long pk = p.p0;
+                    if (mid > 0) {
+                        const int ic = p.in_counter0 + (int) mid;
+                        const double np = __ddiv_rn(__dmul_rn(__dadd_rn((double) ic, p.in_pos_shift), p.ssr), p.dsr);
+                        pk = p.p0 + (__double2int_rz(np) - p.in_pos_int0);
+                    }
+                    if (pk >= lim[t]) hi = mid;
+                    else lo = mid + 1;
+                }
+                s_j[t] = (int) lo;
+            }
+        }
+        __syncthreads();
+        const int ka = s_j[0], kb = s_j[1];
+        for (int k = ka + tid; k < kb; k += FNT) {
+            long long ip = p.p0;
+            double fpos = p.fpos0;
+            if (k > 0) {
+                const int ic = p.in_counter0 + k;
+                const double np = __ddiv_rn(__dmul_rn(__dadd_rn((double) ic, p.in_pos_shift), p.ssr), p.dsr);
+                const int ni = __double2int_rz(np);
+                ip = p.p0 + (ni - p.in_pos_int0);
+                fpos = __dsub_rn(np, (double) ni);
+            }
+            double x = __dmul_rn(fpos, (double) p.fracs);
+            const int fti = __double2int_rz(x);
+            x = __dsub_rn(x, (double) fti);
+            const double x2 = __dmul_rn(x, x);
+            const double* __restrict__ b = p.bank + (long long) fti * p.flen * 3;
+            const long long ws = ip - p.fll;
+            const bool use_b = ws >= bsel;
+            const double* yp = use_b ? ybuf_b : ya;
+            const int yi = (int) (ws - (use_b ? yb0 : ya0));
+            if (yi < 0 || yi + p.flen > YMAX) continue; // cannot happen for owned outputs
+            double acc = 0.0;
+            for (int i = 0; i < p.flen; i++) {
+                const double c = fma(__ldg(b + 3 * i + 2), x2, fma(__ldg(b + 3 * i + 1), x, __ldg(b + 3 * i)));
+                acc = fma(c, yp[ylay(yi + i, p.ysh)], acc);
+            }
+            dst_write_f(dst, ch, p.e0 + k, acc);
+        }
+    }
+}
+
+int fused_smem_bytes(int bank_doubles_in_smem)
+{
+    return 2 * FPL * (int) sizeof(double2) + 256 * (int) sizeof(double2) + bank_doubles_in_smem * (int) sizeof(double);
+}
+
+int fused_max_span(int lg, int yl, int yr) { return 2 * (FM - 2 * lg) - yl - yr; }
+
+void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
+{
+    if (p.n_tiles <= 0 || n_ch <= 0) return;
+    const int smem = fused_smem_bytes(p.bank_in_smem ? p.bank_len : 0);
+    static bool configured[16][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !configured[dev][p.mode]) {
+        if (p.mode == 0)
+            cudaFuncSetAttribute(k_up2_frac<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        else
+            cudaFuncSetAttribute(k_up2_frac<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        configured[dev][p.mode] = true;
+    }
+    const int n_pairs = (p.n_tiles + 1) >> 1;
+    if (p.mode == 0) k_up2_frac<0><<<(unsigned) (n_pairs * n_ch), FNT, smem, st>>>(p, src, dst);
+    else k_up2_frac<1><<<(unsigned) (n_pairs * n_ch), FNT, smem, st>>>(p, src, dst);
+}
+
+} // namespace r8bgpu

@@ -61,6 +61,36 @@ struct HbParams {
     double taps[14];
 };
 
+// Fused 2x BlockConvolver + fractional interpolator (r8b_fused.cu).  Positions are indices of the
+// 2x-rate stream between the two stages.
+struct FusedParams {
+    int mode;              // 0 whole stepping, 1 order-2 bank
+    int n_tiles;           // tiles of `span` owned positions each, processed in pairs
+    int span;              // even
+    long long p_lo, p_hi;  // owned position range of this call [p_lo, p_hi), p_lo even
+    int yl;                // left margin of a tile's valid range (>= fll, even)
+    int lg;                // half support of the polyphase low-pass, input samples
+    int ysh;               // y layout: index i lives at i + (i >> ysh) (31 = plain)
+    const double2* spec;   // low-pass spectrum, slot order, pre-scaled by 1/(2M)
+    const double2* tw;     // exp(-2*pi*i*k/M)
+    // interpolator
+    const double* bank;
+    int bank_len, bank_in_smem;
+    int flen, fll;
+    long long e0, e1;      // outputs of this call
+    int in_step, out_step;
+    const int* phase_off;  // [out_step] floor(r*in_step/out_step)
+    const int* phase_row;  // [out_step] (r*in_step) % out_step
+    int fracs;
+    double ssr, dsr;
+    int in_counter0, in_pos_int0;
+    double in_pos_shift, fpos0;
+    long long p0;
+};
+int fused_smem_bytes(int bank_doubles_in_smem);
+int fused_max_span(int lg, int yl, int yr);
+void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st);
+
 int blockconv_smem_bytes(int fft_log2, int up);
 cudaError_t blockconv_configure(); // opt-in shared memory attributes; call once per device
 

@@ -54,7 +54,7 @@ bool make_blockconv(StageDesc& s, double norm_freq, double tb, double atten, dou
     s.ref_prev_len = prev_len;
     s.latency = latency;
     const int lg = (L + up - 1) / up + 1;
-    s.src_history = (latency + L + up - 1) / up + lg + 8;
+    s.src_history = (latency + L + up - 1) / up + lg + 40;
     if (s.block_exact) s.src_history = 2 * b2 + 16;
     return true;
 }
@@ -493,6 +493,14 @@ int Schedule::advance(int l, std::vector<StageCall>& calls)
                 cnt = lo + 1;
             }
             e1 = c.e0 + cnt;
+            c.p_last = ps.p;
+            if (cnt > 1) {
+                long long p;
+                int ni;
+                double f;
+                poly_pos(ps, s.src_rate, s.dst_rate, cnt - 1, p, ni, f);
+                c.p_last = p;
+            }
             if (cnt > 0) {
                 long long p;
                 int ni;

@@ -93,6 +93,7 @@ struct StageCall {
     int in_counter0 = 0, in_pos_int0 = 0;
     double in_pos_shift = 0.0, fpos0 = 0.0;
     long long p0 = 0;
+    long long p_last = 0; // read position of the last output of this call (FracPoly)
 };
 
 struct Schedule {
