@@ -47,8 +47,17 @@ constexpr int IQ = 3;               // ... x stepping cycles per lane
 
 __device__ __forceinline__ int ylay(int i, int ysh) { return i + (i >> ysh); }
 
+// W_M^idx (idx < M) from two 64-entry shared-memory tables: W^idx = W^(64a) * W^b, idx = 64a + b.
+// One extra complex multiply (<= ~1.5 ulp) instead of a 64 KB table walked through L1/L2.
+__device__ __forceinline__ double2 tw_split(const double2* __restrict__ twc, const double2* __restrict__ twf, int idx)
+{
+    const double2 c = twc[idx >> 6], f = twf[idx & 63];
+    return make_double2(fma(c.x, f.x, -c.y * f.y), fma(c.x, f.y, c.y * f.x));
+}
+
 // forward pass 1 fused with the gather from global memory (radix 16, NCUR = M, D = 256)
-__device__ __forceinline__ void fwd_pass1_gather(double2* __restrict__ s, const double2* __restrict__ tw,
+__device__ __forceinline__ void fwd_pass1_gather(double2* __restrict__ s, const double2* __restrict__ twc,
+                                                 const double2* __restrict__ twf,
                                                  const SrcView& src, int ch, long long wa, long long wb,
                                                  bool has_b, int r)
 {
@@ -63,7 +72,7 @@ __device__ __forceinline__ void fwd_pass1_gather(double2* __restrict__ s, const 
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         double2 x = v[bitrev<16>(q)];
-        if (q > 0) x = cmul<+1>(x, __ldg(&tw[r * q]));
+        if (q > 0) x = cmul<+1>(x, tw_split(twc, twf, r * q));
         s[fft_pad(r + q * 256)] = x;
     }
 }
@@ -106,6 +115,147 @@ __device__ __forceinline__ void inv_pass(double2* __restrict__ s, const double2*
     for (int j = 0; j < 16; j++) s[fft_pad(base + j * D)] = v[bitrev<16>(j)];
 }
 
+
+// Whole-stepping interpolation of one tile pair out of shared memory.  Task = (group of IR
+// consecutive output phases) x (chunk of 32*IQ stepping cycles); lane = cycle, so the y reads of
+// a warp are in_step doubles apart (conflict-free: odd stride, or made odd by the PAD layout) and the
+// bank reads are warp-uniform broadcasts.  The tap loop is split into a predicated ramp-up, a
+// branch-free middle where all IR phases are active, and a predicated ramp-down.
+template <bool PAD, bool BANK_SMEM>
+__device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView& dst, int ch,
+                                             const double* __restrict__ smd, int off_a, int off_b,
+                                             long long ya0, long long yb0, long long bsel, long long A0,
+                                             long long B1, const double* __restrict__ bank, int tid)
+{
+    constexpr int YMAX = 2 * FM;
+    long long ja = (A0 * p.out_step + p.in_step - 1) / p.in_step;
+    long long jb = (B1 * p.out_step + p.in_step - 1) / p.in_step;
+    if (ja < p.e0) ja = p.e0;
+    if (jb > p.e1) jb = p.e1;
+    if (jb <= ja) return;
+    const long long c_first = ja / p.out_step, c_last = (jb - 1) / p.out_step;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int n_groups = (p.out_step + IR - 1) / IR;
+    const int n_chunks = (int) ((c_last - c_first + 32 * IQ) / (32 * IQ));
+    const int n_tasks = n_groups * n_chunks;
+    const int flen = p.flen;
+    for (int task = warp; task < n_tasks; task += FNT / 32) {
+        const int grp = task % n_groups, chunk = task / n_groups;
+        const int r0 = grp * IR;
+        int d[IR];
+        const double* br[IR]; // bank row pointer biased by -d[r]: tap (s - d[r]) of phase r is br[r][s]
+        const int o0 = __ldg(&p.phase_off[r0]);
+#pragma unroll
+        for (int r = 0; r < IR; r++) {
+            const int rr = (r0 + r < p.out_step) ? r0 + r : p.out_step - 1;
+            d[r] = __ldg(&p.phase_off[rr]) - o0;
+            br[r] = bank + (__ldg(&p.phase_row[rr]) * flen - d[r]);
+        }
+        const int dmax = d[IR - 1];
+        const int smax = dmax + flen;
+        long long cq[IQ];
+        int yo[IQ];
+#pragma unroll
+        for (int q = 0; q < IQ; q++) {
+            cq[q] = c_first + (long long) chunk * (32 * IQ) + q * 32 + lane;
+            const long long c = cq[q] <= c_last ? cq[q] : c_last;
+            const long long ws = c * p.in_step + o0 - p.fll;
+            const bool use_b = ws >= bsel;
+            long long li = ws - (use_b ? yb0 : ya0);
+            if (li < 0) li = 0; // edge-cycle phases this pair does not own: never stored
+            if (li > YMAX - smax) li = YMAX - smax;
+            yo[q] = (int) li + (PAD ? 0 : (use_b ? off_b : off_a));
+            if (PAD) yo[q] |= use_b ? 0 : (1 << 30); // buffer select kept in bit 30 (layout applied per load)
+        }
+        auto yload = [&](int q, int s) -> double {
+            if (!PAD) return smd[yo[q] + s];
+            const int i = (yo[q] & ~(1 << 30)) + s;
+            return smd[((yo[q] >> 30) ? off_a : off_b) + i + (i >> p.ysh)];
+        };
+        double acc[IR][IQ];
+#pragma unroll
+        for (int r = 0; r < IR; r++)
+#pragma unroll
+            for (int q = 0; q < IQ; q++) acc[r][q] = 0.0;
+        const int mid0 = dmax < flen ? dmax : flen, mid1 = dmax < flen ? flen : dmax;
+        int s = 0;
+#pragma unroll 1
+        for (; s < mid0; s++) { // ramp-up: phases with d[r] <= s
+            double yv[IQ];
+#pragma unroll
+            for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
+#pragma unroll
+            for (int r = 0; r < IR; r++)
+                if (d[r] <= s) {
+                    const double b = br[r][s];
+#pragma unroll
+                    for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
+                }
+        }
+        if (dmax < flen) {
+#pragma unroll 4
+            for (; s < mid1; s++) { // every phase active: no predicates
+                double yv[IQ];
+#pragma unroll
+                for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
+#pragma unroll
+                for (int r = 0; r < IR; r++) {
+                    const double b = br[r][s];
+#pragma unroll
+                    for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (; s < mid1; s++) { // sparse case (d spans more than one filter length)
+                double yv[IQ];
+#pragma unroll
+                for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
+#pragma unroll
+                for (int r = 0; r < IR; r++)
+                    if ((unsigned) (s - d[r]) < (unsigned) flen) {
+                        const double b = br[r][s];
+#pragma unroll
+                        for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
+                    }
+            }
+        }
+#pragma unroll 1
+        for (; s < smax; s++) { // ramp-down: phases with s - d[r] < flen
+            double yv[IQ];
+#pragma unroll
+            for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
+#pragma unroll
+            for (int r = 0; r < IR; r++)
+                if (s - d[r] < flen) {
+                    const double b = br[r][s];
+#pragma unroll
+                    for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
+                }
+        }
+        // each lane owns IR consecutive outputs per cycle: 128-bit stores when the destination allows
+        const bool vec_ok = (dst.mask == -1) && ((dst.stride & 1) == 0) &&
+            ((reinterpret_cast<unsigned long long>(dst.ptr) & 15) == 0);
+#pragma unroll
+        for (int q = 0; q < IQ; q++) {
+            if (cq[q] > c_last) continue;
+            const long long j0 = cq[q] * p.out_step + r0;
+            const bool full = (r0 + IR <= p.out_step) && j0 >= ja && j0 + IR <= jb;
+            if (full && vec_ok && (((j0 - dst.base) & 1) == 0)) {
+                double2* o = reinterpret_cast<double2*>(dst.ptr + (long long) ch * dst.stride + (j0 - dst.base));
+#pragma unroll
+                for (int r = 0; r < IR; r += 2) o[r >> 1] = make_double2(acc[r][q], acc[r + 1][q]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < IR; r++) {
+                    const long long j = j0 + r;
+                    if (r0 + r < p.out_step && j >= ja && j < jb) dst_write_f(dst, ch, j, acc[r][q]);
+                }
+            }
+        }
+    }
+}
+
 } // namespace
 
 // MODE 0: whole stepping, MODE 1: order-2 polynomial bank.
@@ -116,7 +266,9 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     double2* bufA = smem;              // forward spectrum Z, later Y_b / y_b
     double2* bufB = smem + FPL;        // Y_a / y_a
     double2* tw2 = smem + 2 * FPL;     // W_256^k, k < 256
-    double* sbank = reinterpret_cast<double*>(tw2 + 256); // whole-step bank (if it fits)
+    double2* twc = tw2 + 256;          // W_M^(64 a), a < 64
+    double2* twf = twc + 64;           // W_M^b, b < 64
+    double* sbank = reinterpret_cast<double*>(twf + 64); // whole-step bank (if it fits)
     __shared__ int s_j[2];
 
     const int tid = threadIdx.x;
@@ -138,10 +290,13 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
 
     // tables into shared memory
     for (int i = tid; i < 256; i += FNT) tw2[i] = __ldg(&p.tw[i * (FM / 256)]);
+    if (tid < 64) twc[tid] = __ldg(&p.tw[tid * 64]);
+    else if (tid < 128) twf[tid - 64] = __ldg(&p.tw[tid - 64]);
+    __syncthreads();
     if (MODE == 0 && p.bank_in_smem)
         for (int i = tid; i < p.bank_len; i += FNT) sbank[i] = __ldg(&p.bank[i]);
 
-    if (tid < 256) fwd_pass1_gather(bufA, p.tw, src, ch, wa, wb, has_b, tid);
+    if (tid < 256) fwd_pass1_gather(bufA, twc, twf, src, ch, wa, wb, has_b, tid);
     __syncthreads();
     if (tid < 256) fwd_pass<256>(bufA, p.tw, tw2, tid);
     __syncthreads();
@@ -183,7 +338,7 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             double2 x = buf[fft_pad(g + q * 256)];
-            if (q > 0) x = cmul<-1>(x, __ldg(&p.tw[g * q]));
+            if (q > 0) x = cmul<-1>(x, tw_split(twc, twf, g * q));
             v[q] = x;
         }
         Network<16, -1>::run(v);
@@ -209,77 +364,14 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     constexpr int YMAX = 2 * FM;                  // doubles per tile buffer (before layout padding)
 
     if (MODE == 0) {
-        // outputs j with A0 <= floor(j*InStep/OutStep) < B1, clipped to [e0,e1)
-        long long ja = (A0 * p.out_step + p.in_step - 1) / p.in_step;
-        long long jb = (B1 * p.out_step + p.in_step - 1) / p.in_step;
-        if (ja < p.e0) ja = p.e0;
-        if (jb > p.e1) jb = p.e1;
-        if (jb <= ja) return;
-        const long long c_first = ja / p.out_step, c_last = (jb - 1) / p.out_step;
-        const int warp = tid >> 5, lane = tid & 31;
-        const int n_groups = (p.out_step + IR - 1) / IR;
-        const int n_chunks = (int) ((c_last - c_first + 32 * IQ) / (32 * IQ));
-        const int n_tasks = n_groups * n_chunks;
-        const double* bank = p.bank_in_smem ? sbank : p.bank;
-        for (int task = warp; task < n_tasks; task += FNT / 32) {
-            const int grp = task % n_groups, chunk = task / n_groups;
-            const int r0 = grp * IR;
-            int d[IR], row[IR];
-            const int o0 = __ldg(&p.phase_off[r0]);
-#pragma unroll
-            for (int r = 0; r < IR; r++) {
-                const int rr = (r0 + r < p.out_step) ? r0 + r : p.out_step - 1;
-                d[r] = __ldg(&p.phase_off[rr]) - o0;
-                row[r] = __ldg(&p.phase_row[rr]) * p.flen;
-            }
-            const int smax = d[IR - 1] + p.flen;
-            const double* yp[IQ];
-            long long cq[IQ];
-            int yi[IQ];
-#pragma unroll
-            for (int q = 0; q < IQ; q++) {
-                cq[q] = c_first + (long long) chunk * (32 * IQ) + q * 32 + lane;
-                long long c = cq[q] <= c_last ? cq[q] : c_last;
-                const long long ws = c * p.in_step + o0 - p.fll; // first y index of the tile window
-                const bool use_b = ws >= bsel;
-                yp[q] = use_b ? ybuf_b : ya;
-                long long li = ws - (use_b ? yb0 : ya0);
-                // phases of the edge cycles that this pair does not own may point outside the tile;
-                // their results are never stored, keep the reads inside the buffer
-                if (li < 0) li = 0;
-                if (li > YMAX - smax) li = YMAX - smax;
-                yi[q] = (int) li;
-            }
-            double acc[IR][IQ];
-#pragma unroll
-            for (int r = 0; r < IR; r++)
-#pragma unroll
-                for (int q = 0; q < IQ; q++) acc[r][q] = 0.0;
-#pragma unroll 1
-            for (int s = 0; s < smax; s++) {
-                double yv[IQ];
-#pragma unroll
-                for (int q = 0; q < IQ; q++) yv[q] = yp[q][ylay(yi[q] + s, p.ysh)];
-#pragma unroll
-                for (int r = 0; r < IR; r++) {
-                    const int i = s - d[r];
-                    if ((unsigned) i < (unsigned) p.flen) {
-                        const double b = bank[row[r] + i];
-#pragma unroll
-                        for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < IQ; q++) {
-                if (cq[q] > c_last) continue;
-                const long long j0 = cq[q] * p.out_step + r0;
-#pragma unroll
-                for (int r = 0; r < IR; r++) {
-                    const long long j = j0 + r;
-                    if (r0 + r < p.out_step && j >= ja && j < jb) dst_write_f(dst, ch, j, acc[r][q]);
-                }
-            }
+        const double* smd = reinterpret_cast<const double*>(smem);
+        const int off_a = 2 * FPL, off_b = 0; // tile a lives in bufB, tile b in bufA (in doubles)
+        if (p.ysh == 31) {
+            if (p.bank_in_smem) interp_whole<false, true>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, sbank, tid);
+            else interp_whole<false, false>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, p.bank, tid);
+        } else {
+            if (p.bank_in_smem) interp_whole<true, true>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, sbank, tid);
+            else interp_whole<true, false>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, p.bank, tid);
         }
     } else {
         // order-2 bank: output k of this call (k >= 0) sits at (p_k, fpos_k); find the pair's k range
@@ -337,7 +429,7 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
 
 int fused_smem_bytes(int bank_doubles_in_smem)
 {
-    return 2 * FPL * (int) sizeof(double2) + 256 * (int) sizeof(double2) + bank_doubles_in_smem * (int) sizeof(double);
+    return 2 * FPL * (int) sizeof(double2) + (256 + 128) * (int) sizeof(double2) + bank_doubles_in_smem * (int) sizeof(double);
 }
 
 int fused_max_span(int lg, int yl, int yr) { return 2 * (FM - 2 * lg) - yl - yr; }
