@@ -143,22 +143,21 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
         const int grp = task % n_groups, chunk = task / n_groups;
         const int r0 = grp * IR;
         int d[IR];
-        const double* br[IR]; // bank row pointer biased by -d[r]: tap (s - d[r]) of phase r is br[r][s]
+        int br[IR]; // bank row offset biased by -d[r]: tap (s - d[r]) of phase r is bank[br[r] + s]
         const int o0 = __ldg(&p.phase_off[r0]);
 #pragma unroll
         for (int r = 0; r < IR; r++) {
             const int rr = (r0 + r < p.out_step) ? r0 + r : p.out_step - 1;
             d[r] = __ldg(&p.phase_off[rr]) - o0;
-            br[r] = bank + (__ldg(&p.phase_row[rr]) * flen - d[r]);
+            br[r] = __ldg(&p.phase_row[rr]) * flen - d[r];
         }
         const int dmax = d[IR - 1];
         const int smax = dmax + flen;
-        long long cq[IQ];
         int yo[IQ];
 #pragma unroll
         for (int q = 0; q < IQ; q++) {
-            cq[q] = c_first + (long long) chunk * (32 * IQ) + q * 32 + lane;
-            const long long c = cq[q] <= c_last ? cq[q] : c_last;
+            const long long cq = c_first + (long long) chunk * (32 * IQ) + q * 32 + lane;
+            const long long c = cq <= c_last ? cq : c_last;
             const long long ws = c * p.in_step + o0 - p.fll;
             const bool use_b = ws >= bsel;
             long long li = ws - (use_b ? yb0 : ya0);
@@ -187,7 +186,7 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
 #pragma unroll
             for (int r = 0; r < IR; r++)
                 if (d[r] <= s) {
-                    const double b = br[r][s];
+                    const double b = bank[br[r] + s];
 #pragma unroll
                     for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
                 }
@@ -200,7 +199,7 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
                 for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
 #pragma unroll
                 for (int r = 0; r < IR; r++) {
-                    const double b = br[r][s];
+                    const double b = bank[br[r] + s];
 #pragma unroll
                     for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
                 }
@@ -214,7 +213,7 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
 #pragma unroll
                 for (int r = 0; r < IR; r++)
                     if ((unsigned) (s - d[r]) < (unsigned) flen) {
-                        const double b = br[r][s];
+                        const double b = bank[br[r] + s];
 #pragma unroll
                         for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
                     }
@@ -228,23 +227,39 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
 #pragma unroll
             for (int r = 0; r < IR; r++)
                 if (s - d[r] < flen) {
-                    const double b = br[r][s];
+                    const double b = bank[br[r] + s];
 #pragma unroll
                     for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
                 }
         }
-        // each lane owns IR consecutive outputs per cycle: 128-bit stores when the destination allows
-        const bool vec_ok = (dst.mask == -1) && ((dst.stride & 1) == 0) &&
-            ((reinterpret_cast<unsigned long long>(dst.ptr) & 15) == 0);
+        // each lane owns IR consecutive outputs per cycle (64 contiguous bytes)
+        const bool linear = (dst.mask == -1);
+        double* const obase = dst.ptr + (long long) ch * dst.stride - dst.base;
 #pragma unroll
         for (int q = 0; q < IQ; q++) {
-            if (cq[q] > c_last) continue;
-            const long long j0 = cq[q] * p.out_step + r0;
+            const long long cqq = c_first + (long long) chunk * (32 * IQ) + q * 32 + lane;
+            if (cqq > c_last) continue;
+            const long long j0 = cqq * p.out_step + r0;
             const bool full = (r0 + IR <= p.out_step) && j0 >= ja && j0 + IR <= jb;
-            if (full && vec_ok && (((j0 - dst.base) & 1) == 0)) {
-                double2* o = reinterpret_cast<double2*>(dst.ptr + (long long) ch * dst.stride + (j0 - dst.base));
+            if (linear) {
+                double* o = obase + j0;
+                if (full) {
+                    if ((reinterpret_cast<unsigned long long>(o) & 15) == 0) {
 #pragma unroll
-                for (int r = 0; r < IR; r += 2) o[r >> 1] = make_double2(acc[r][q], acc[r + 1][q]);
+                        for (int r = 0; r < IR; r += 2)
+                            *reinterpret_cast<double2*>(o + r) = make_double2(acc[r][q], acc[r + 1][q]);
+                    } else { // 8-byte aligned start: scalar head and tail, aligned pairs in between
+                        o[0] = acc[0][q];
+#pragma unroll
+                        for (int r = 1; r + 1 < IR; r += 2)
+                            *reinterpret_cast<double2*>(o + r) = make_double2(acc[r][q], acc[r + 1][q]);
+                        o[IR - 1] = acc[IR - 1][q];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < IR; r++)
+                        if (r0 + r < p.out_step && j0 + r >= ja && j0 + r < jb) o[r] = acc[r][q];
+                }
             } else {
 #pragma unroll
                 for (int r = 0; r < IR; r++) {
@@ -303,24 +318,35 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     if (tid < 256) fwd_pass<16>(bufA, p.tw, tw2, tid);
     __syncthreads();
 
-    // C. frequency pairs
-    for (int s1 = tid; s1 < FM; s1 += FNT) {
-        const int k = freq_of<FM>(s1);
-        if (k > FM / 2) continue;
-        const int k2 = (FM - k) & (FM - 1);
-        const int s2 = slot_of<FM>(k2);
-        const double2 z1 = bufA[fft_pad(s1)];
-        const double2 z2 = bufA[fft_pad(s2)];
-        const double2 g1 = __ldg(&p.spec[s1]);
-        const double2 g2 = __ldg(&p.spec[s2]);
-        // X_a[k] = z1 + conj z2 (the 1/2 lives in G); X_a[M-k] = conj X_a[k]
-        const double2 xa = make_double2(z1.x + z2.x, z1.y - z2.y);
-        const double2 xb = make_double2(z1.y + z2.y, z2.x - z1.x); // -i (z1 - conj z2)
-        bufB[fft_pad(s1)] = cmul<+1>(xa, g1);
-        bufA[fft_pad(s1)] = cmul<+1>(xb, g1);
-        if (s2 != s1) {
-            bufB[fft_pad(s2)] = cmul<+1>(make_double2(xa.x, -xa.y), g2);
-            bufA[fft_pad(s2)] = cmul<+1>(make_double2(xb.x, -xb.y), g2);
+    // C. frequency pairs (all spectrum loads issued before the first use)
+    {
+        constexpr int NC = FM / FNT;
+        double2 g1[NC], g2[NC];
+        int s2v[NC];
+#pragma unroll
+        for (int u = 0; u < NC; u++) {
+            const int s1 = tid + u * FNT;
+            const int k = freq_of<FM>(s1);
+            const int s2 = slot_of<FM>((FM - k) & (FM - 1));
+            s2v[u] = (k > FM / 2) ? -1 : s2;
+            g1[u] = __ldg(&p.spec[s1]);
+            g2[u] = __ldg(&p.spec[s2]);
+        }
+#pragma unroll
+        for (int u = 0; u < NC; u++) {
+            if (s2v[u] < 0) continue;
+            const int s1 = tid + u * FNT, s2 = s2v[u];
+            const double2 z1 = bufA[fft_pad(s1)];
+            const double2 z2 = bufA[fft_pad(s2)];
+            // X_a[k] = z1 + conj z2 (the 1/2 lives in G); X_a[M-k] = conj X_a[k]
+            const double2 xa = make_double2(z1.x + z2.x, z1.y - z2.y);
+            const double2 xb = make_double2(z1.y + z2.y, z2.x - z1.x); // -i (z1 - conj z2)
+            bufB[fft_pad(s1)] = cmul<+1>(xa, g1[u]);
+            bufA[fft_pad(s1)] = cmul<+1>(xb, g1[u]);
+            if (s2 != s1) {
+                bufB[fft_pad(s2)] = cmul<+1>(make_double2(xa.x, -xa.y), g2[u]);
+                bufA[fft_pad(s2)] = cmul<+1>(make_double2(xb.x, -xb.y), g2[u]);
+            }
         }
     }
     __syncthreads();
