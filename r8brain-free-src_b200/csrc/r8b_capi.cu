@@ -190,9 +190,12 @@ struct r8bgpu_batch {
     std::vector<EvPair> events;
     std::vector<double> stage_ms;
     std::vector<unsigned long long> stage_launches;
-    // staging for the host-pointer entry point
+    // staging + pipeline resources for the host-pointer entry point
     double* st_in = nullptr;
     double* st_out = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;
+    int host_groups = 1;
+    std::vector<cudaEvent_t> ev_h2d, ev_k;
 
     ~r8bgpu_batch()
     {
@@ -207,6 +210,11 @@ struct r8bgpu_batch {
         }
         cudaFree(st_in);
         cudaFree(st_out);
+        for (auto e : ev_h2d) cudaEventDestroy(e);
+        for (auto e : ev_k) cudaEventDestroy(e);
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
+        if (s_comp) cudaStreamDestroy(s_comp);
     }
 };
 
@@ -529,6 +537,9 @@ int r8bgpu_batch_clear(r8bgpu_batch* b)
                      "batch_clear: cudaMemsetAsync"))
             return -1;
     }
+    // clear() is rare; finishing it here keeps the device path (batch stream) and the host path
+    // (internal pipeline streams) ordered without cross-stream events
+    if (!cuda_ok(cudaStreamSynchronize(b->stream), "batch_clear: sync")) return -1;
     return 0;
 }
 
@@ -538,41 +549,12 @@ int r8bgpu_batch_sync(r8bgpu_batch* b)
     return cuda_ok(cudaStreamSynchronize(b->stream), "batch_sync") ? 0 : -1;
 }
 
-int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, int l, double* d_out,
-                         size_t out_stride, int out_cap)
+// Launches every kernel of one process() call (already scheduled in b->calls) for the channel range
+// [ch0, ch0+nch) on stream st.  d_in / d_out point at the FIRST channel of that range.
+static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, int l, double* d_out,
+                        size_t out_stride, int ch0, int nch, cudaStream_t st)
 {
-    if (b == nullptr || l < 0 || l > b->plan->max_in_len) {
-        set_err("batch_process: l must be in [0, MaxInLen]");
-        return -1;
-    }
-    if (l > 0 && d_in == nullptr) {
-        set_err("batch_process: null input");
-        return -1;
-    }
-    DeviceGuard g(b->device);
     const Plan& P = *b->plan;
-    const cudaStream_t st = b->stream;
-    if (P.passthrough) { // SrcSampleRate == DstSampleRate: the reference hands the input back
-        if (l > out_cap) {
-            set_err("batch_process: output capacity too small");
-            return -1;
-        }
-        if (l > 0 && !cuda_ok(cudaMemcpy2DAsync(d_out, out_stride * sizeof(double), d_in,
-                                                in_stride * sizeof(double), (size_t) l * sizeof(double),
-                                                (size_t) b->n_ch, cudaMemcpyDeviceToDevice, st),
-                              "batch_process: passthrough copy"))
-            return -1;
-        return l;
-    }
-
-    Schedule saved = b->sched;
-    const int n_out = b->sched.advance(l, b->calls);
-    if (n_out > out_cap || (n_out > 0 && d_out == nullptr)) {
-        b->sched = saved;
-        set_err("batch_process: output capacity too small for this call");
-        return -1;
-    }
-
     const size_t ns = P.stages.size();
     for (size_t i = 0; i < ns; i++) {
         const StageDesc& s = P.stages[i];
@@ -582,7 +564,7 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
         const bool fused = d.fused_with_next;
         if ((fused ? b->calls[i + 1].e1 <= b->calls[i + 1].e0 : c.e1 <= c.e0)) continue;
         SrcView src;
-        src.ring = d.ring;
+        src.ring = d.ring + (long long) ch0 * d.ring_cap;
         src.ring_stride = d.ring_cap;
         src.ring_mask = d.ring_cap - 1;
         if (i == 0) {
@@ -603,7 +585,7 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
             dst.mask = -1;
             dst.base = b->calls[last].e0;
         } else {
-            dst.ptr = b->dev[last + 1].ring;
+            dst.ptr = b->dev[last + 1].ring + (long long) ch0 * b->dev[last + 1].ring_cap;
             dst.stride = b->dev[last + 1].ring_cap;
             dst.mask = b->dev[last + 1].ring_cap - 1;
             dst.base = 0;
@@ -658,7 +640,7 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
             p.in_pos_shift = fc.in_pos_shift;
             p.fpos0 = fc.fpos0;
             p.p0 = fc.p0;
-            launch_up2_frac(p, src, dst, b->n_ch, st);
+            launch_up2_frac(p, src, dst, nch, st);
             b->launches++;
         } else
         switch (s.kind) {
@@ -691,7 +673,7 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
             p.nyq_gain = d.nyq_gain;
             p.spec = d.spec;
             p.tw = d.tw;
-            launch_blockconv(p, src, dst, b->n_ch, st);
+            launch_blockconv(p, src, dst, nch, st);
             b->launches++;
             break;
         }
@@ -714,8 +696,8 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
             p.in_pos_shift = c.in_pos_shift;
             p.fpos0 = c.fpos0;
             p.p0 = c.p0;
-            if (s.kind == ST_FRAC_WHOLE) launch_frac_whole(p, src, dst, b->n_ch, st);
-            else launch_frac_poly(p, src, dst, b->n_ch, st);
+            if (s.kind == ST_FRAC_WHOLE) launch_frac_whole(p, src, dst, nch, st);
+            else launch_frac_poly(p, src, dst, nch, st);
             b->launches++;
             break;
         }
@@ -727,8 +709,8 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
             p.e0 = c.e0;
             p.e1 = c.e1;
             for (int k = 0; k < s.hb_taps; k++) p.taps[k] = s.hb[(size_t) k];
-            if (s.kind == ST_HBUP) launch_hbup(p, src, dst, b->n_ch, st);
-            else launch_hbdown(p, src, dst, b->n_ch, st);
+            if (s.kind == ST_HBUP) launch_hbup(p, src, dst, nch, st);
+            else launch_hbdown(p, src, dst, nch, st);
             b->launches++;
             break;
         }
@@ -744,14 +726,56 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
         const StageDev& d0 = b->dev[0];
         long long from = c0.n1 - d0.ring_cap;
         if (from < c0.n0) from = c0.n0;
-        launch_save_tail(d_in, (long long) in_stride, c0.n0, from, c0.n1, d0.ring, d0.ring_cap,
-                         d0.ring_cap - 1, b->n_ch, st);
+        launch_save_tail(d_in, (long long) in_stride, c0.n0, from, c0.n1, d0.ring + (long long) ch0 * d0.ring_cap, d0.ring_cap,
+                         d0.ring_cap - 1, nch, st);
         b->launches++;
     }
+}
+
+int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, int l, double* d_out,
+                         size_t out_stride, int out_cap)
+{
+    if (b == nullptr || l < 0 || l > b->plan->max_in_len) {
+        set_err("batch_process: l must be in [0, MaxInLen]");
+        return -1;
+    }
+    if (l > 0 && d_in == nullptr) {
+        set_err("batch_process: null input");
+        return -1;
+    }
+    DeviceGuard g(b->device);
+    const Plan& P = *b->plan;
+    const cudaStream_t st = b->stream;
+    if (P.passthrough) { // SrcSampleRate == DstSampleRate: the reference hands the input back
+        if (l > out_cap) {
+            set_err("batch_process: output capacity too small");
+            return -1;
+        }
+        if (l > 0 && !cuda_ok(cudaMemcpy2DAsync(d_out, out_stride * sizeof(double), d_in,
+                                                in_stride * sizeof(double), (size_t) l * sizeof(double),
+                                                (size_t) b->n_ch, cudaMemcpyDeviceToDevice, st),
+                              "batch_process: passthrough copy"))
+            return -1;
+        return l;
+    }
+
+    Schedule saved = b->sched;
+    const int n_out = b->sched.advance(l, b->calls);
+    if (n_out > out_cap || (n_out > 0 && d_out == nullptr)) {
+        b->sched = saved;
+        set_err("batch_process: output capacity too small for this call");
+        return -1;
+    }
+
+    launch_call(b, d_in, in_stride, l, d_out, out_stride, 0, b->n_ch, st);
     if (!cuda_ok(cudaGetLastError(), "batch_process: kernel launch")) return -1;
     return n_out;
 }
 
+// Host-pointer path.  The batch is cut into channel groups that flow through a three-stage pipeline
+//   copy stream A: H2D(group g+1)  |  compute stream: kernels(group g)  |  copy stream B: D2H(group g-1)
+// so the two PCIe directions and the SMs work at the same time (channels are independent, so a group
+// is a self-contained sub-batch).  Staging buffers are per channel, so groups never alias.
 int r8bgpu_batch_process_host(r8bgpu_batch* b, const double* h_in, size_t in_stride, int l, double* h_out,
                               size_t out_stride, int out_cap)
 {
@@ -759,31 +783,80 @@ int r8bgpu_batch_process_host(r8bgpu_batch* b, const double* h_in, size_t in_str
         set_err("batch_process_host: l must be in [0, MaxInLen]");
         return -1;
     }
+    if (l > 0 && h_in == nullptr) {
+        set_err("batch_process_host: null input");
+        return -1;
+    }
     DeviceGuard g(b->device);
-    const size_t in_cap = (size_t) b->plan->max_in_len;
-    const size_t o_cap = (size_t) b->plan->max_out_len;
+    const Plan& P = *b->plan;
+    const size_t in_cap = (size_t) P.max_in_len;
+    const size_t o_cap = ((size_t) P.max_out_len + 3) & ~(size_t) 3; // rows 32-byte aligned
     if (b->st_in == nullptr) {
         if (!cuda_ok(cudaMalloc(&b->st_in, in_cap * b->n_ch * sizeof(double)), "process_host: cudaMalloc(in)")) return -1;
         if (!cuda_ok(cudaMalloc(&b->st_out, o_cap * b->n_ch * sizeof(double)), "process_host: cudaMalloc(out)")) return -1;
         b->dev_bytes += (in_cap + o_cap) * b->n_ch * sizeof(double);
+        if (!cuda_ok(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking), "process_host: stream")) return -1;
+        if (!cuda_ok(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking), "process_host: stream")) return -1;
+        if (!cuda_ok(cudaStreamCreateWithFlags(&b->s_comp, cudaStreamNonBlocking), "process_host: stream")) return -1;
+        int groups = 8;
+        if (const char* e = getenv("R8BGPU_HOST_GROUPS")) groups = atoi(e);
+        if (groups < 1) groups = 1;
+        while (groups > 1 && b->n_ch / groups < 32) groups /= 2; // keep every group a full-GPU launch
+        b->host_groups = groups;
+        b->ev_h2d.resize((size_t) groups);
+        b->ev_k.resize((size_t) groups);
+        for (int i = 0; i < groups; i++) {
+            cudaEventCreateWithFlags(&b->ev_h2d[(size_t) i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&b->ev_k[(size_t) i], cudaEventDisableTiming);
+        }
     }
-    if (l > 0 && !cuda_ok(cudaMemcpy2DAsync(b->st_in, in_cap * sizeof(double), h_in, in_stride * sizeof(double),
-                                            (size_t) l * sizeof(double), (size_t) b->n_ch,
-                                            cudaMemcpyHostToDevice, b->stream),
-                          "process_host: H2D"))
-        return -1;
-    const int n = r8bgpu_batch_process(b, b->st_in, in_cap, l, b->st_out, o_cap, (int) o_cap);
-    if (n < 0) return n;
-    if (n > out_cap) {
+    int n = l;
+    if (!P.passthrough) {
+        Schedule saved = b->sched;
+        n = b->sched.advance(l, b->calls);
+        if (n > out_cap || (n > 0 && h_out == nullptr)) {
+            b->sched = saved;
+            set_err("process_host: output capacity too small for this call");
+            return -1;
+        }
+    } else if (l > out_cap) {
         set_err("process_host: output capacity too small");
         return -1;
     }
-    if (n > 0 && !cuda_ok(cudaMemcpy2DAsync(h_out, out_stride * sizeof(double), b->st_out, o_cap * sizeof(double),
-                                            (size_t) n * sizeof(double), (size_t) b->n_ch,
-                                            cudaMemcpyDeviceToHost, b->stream),
-                          "process_host: D2H"))
-        return -1;
-    if (!cuda_ok(cudaStreamSynchronize(b->stream), "process_host: sync")) return -1;
+    // order after any device-path work queued on the batch stream (the two paths share the rings)
+    if (!cuda_ok(cudaStreamSynchronize(b->stream), "process_host: sync(batch stream)")) return -1;
+    const int G = b->host_groups;
+    for (int gi = 0; gi < G; gi++) {
+        const int ch0 = (int) ((long long) b->n_ch * gi / G);
+        const int ch1 = (int) ((long long) b->n_ch * (gi + 1) / G);
+        const int nch = ch1 - ch0;
+        if (nch <= 0) continue;
+        double* din = b->st_in + (size_t) ch0 * in_cap;
+        double* dout = b->st_out + (size_t) ch0 * o_cap;
+        if (l > 0 && !cuda_ok(cudaMemcpy2DAsync(din, in_cap * sizeof(double), h_in + (size_t) ch0 * in_stride,
+                                                in_stride * sizeof(double), (size_t) l * sizeof(double),
+                                                (size_t) nch, cudaMemcpyHostToDevice, b->s_h2d),
+                              "process_host: H2D"))
+            return -1;
+        cudaEventRecord(b->ev_h2d[(size_t) gi], b->s_h2d);
+        cudaStreamWaitEvent(b->s_comp, b->ev_h2d[(size_t) gi], 0);
+        if (P.passthrough) {
+            if (l > 0) cudaMemcpy2DAsync(dout, o_cap * sizeof(double), din, in_cap * sizeof(double),
+                                         (size_t) l * sizeof(double), (size_t) nch, cudaMemcpyDeviceToDevice, b->s_comp);
+        } else {
+            launch_call(b, din, in_cap, l, dout, o_cap, ch0, nch, b->s_comp);
+        }
+        cudaEventRecord(b->ev_k[(size_t) gi], b->s_comp);
+        cudaStreamWaitEvent(b->s_d2h, b->ev_k[(size_t) gi], 0);
+        if (n > 0 && !cuda_ok(cudaMemcpy2DAsync(h_out + (size_t) ch0 * out_stride, out_stride * sizeof(double), dout,
+                                                o_cap * sizeof(double), (size_t) n * sizeof(double), (size_t) nch,
+                                                cudaMemcpyDeviceToHost, b->s_d2h),
+                              "process_host: D2H"))
+            return -1;
+    }
+    if (!cuda_ok(cudaStreamSynchronize(b->s_d2h), "process_host: sync")) return -1;
+    if (!cuda_ok(cudaStreamSynchronize(b->s_comp), "process_host: sync")) return -1;
+    if (!cuda_ok(cudaGetLastError(), "process_host: kernel launch")) return -1;
     return n;
 }
 

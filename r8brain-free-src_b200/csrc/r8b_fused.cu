@@ -62,11 +62,24 @@ __device__ __forceinline__ void fwd_pass1_gather(double2* __restrict__ s, const 
                                                  bool has_b, int r)
 {
     double2 v[16];
+    // Interior tiles lie completely inside the caller's block: plain coalesced loads.  Only the
+    // first tiles of a call reach back into the history ring (or ahead of the available input).
+    const bool fast = wa >= src.cur_base && wb + FM <= src.avail && has_b;
+    if (fast) {
+        const double* __restrict__ pa = src.cur + (long long) ch * src.cur_stride + (wa - src.cur_base) + r;
+        const double* __restrict__ pb = pa + (wb - wa);
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const int n = r + 256 * j;
-        v[j].x = src_read_f(src, ch, wa + n);
-        v[j].y = has_b ? src_read_f(src, ch, wb + n) : 0.0;
+        for (int j = 0; j < 16; j++) {
+            v[j].x = __ldg(pa + 256 * j);
+            v[j].y = __ldg(pb + 256 * j);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int n = r + 256 * j;
+            v[j].x = src_read_f(src, ch, wa + n);
+            v[j].y = has_b ? src_read_f(src, ch, wb + n) : 0.0;
+        }
     }
     Network<16, +1>::run(v);
 #pragma unroll
@@ -128,12 +141,21 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
                                              long long B1, const double* __restrict__ bank, int tid)
 {
     constexpr int YMAX = 2 * FM;
-    long long ja = (A0 * p.out_step + p.in_step - 1) / p.in_step;
-    long long jb = (B1 * p.out_step + p.in_step - 1) / p.in_step;
-    if (ja < p.e0) ja = p.e0;
-    if (jb > p.e1) jb = p.e1;
+    __shared__ long long s_rng[4];
+    if (tid == 0) { // 64-bit divisions once per CTA, not once per thread
+        long long a = (A0 * p.out_step + p.in_step - 1) / p.in_step;
+        long long b = (B1 * p.out_step + p.in_step - 1) / p.in_step;
+        if (a < p.e0) a = p.e0;
+        if (b > p.e1) b = p.e1;
+        s_rng[0] = a;
+        s_rng[1] = b;
+        s_rng[2] = b > a ? a / p.out_step : 0;
+        s_rng[3] = b > a ? (b - 1) / p.out_step : 0;
+    }
+    __syncthreads();
+    const long long ja = s_rng[0], jb = s_rng[1];
     if (jb <= ja) return;
-    const long long c_first = ja / p.out_step, c_last = (jb - 1) / p.out_step;
+    const long long c_first = s_rng[2], c_last = s_rng[3];
     const int warp = tid >> 5, lane = tid & 31;
     const int n_groups = (p.out_step + IR - 1) / IR;
     const int n_chunks = (int) ((c_last - c_first + 32 * IQ) / (32 * IQ));
