@@ -9,6 +9,7 @@
 // delay bank.  All integer scheduling state lives on the host (Schedule), once per batch.
 #include "../../include/r8bgpu.h"
 
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -161,6 +162,9 @@ struct StageDev {
     bool fused_into_prev = false; // on the FRAC stage (its source ring is never materialised)
     int* phase_off = nullptr;
     int* phase_row = nullptr;
+    double* gbank = nullptr; // whole stepping: grouped, pre-shifted, zero-padded bank (see FusedParams)
+    int* goff = nullptr;
+    int gbank_len = 0, smaxp = 0;
     int yl = 0, yr = 0, ysh = 31, span_max = 0, bank_in_smem = 0;
 };
 
@@ -207,6 +211,8 @@ struct r8bgpu_batch {
             cudaFree(d.ring);
             cudaFree(d.phase_off);
             cudaFree(d.phase_row);
+            cudaFree(d.gbank);
+            cudaFree(d.goff);
         }
         cudaFree(st_in);
         cudaFree(st_out);
@@ -466,7 +472,36 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 if (!cuda_ok(cudaMalloc(&d.phase_row, tb), "cudaMalloc(phase)")) return nullptr;
                 cudaMemcpy(d.phase_off, off.data(), tb, cudaMemcpyHostToDevice);
                 cudaMemcpy(d.phase_row, row.data(), tb, cudaMemcpyHostToDevice);
-                d.bank_in_smem = (fused_smem_bytes((int) s.bank.table.size()) <= 220 * 1024) ? 1 : 0;
+                // grouped bank for the fused kernel: 8 consecutive phases share one y window
+                {
+                    const int flen = s.bank.filter_len, ng = (s.out_step + 7) / 8;
+                    int dmax = 0;
+                    for (int g = 0; g < ng; g++) {
+                        const int r1 = std::min(g * 8 + 7, s.out_step - 1);
+                        dmax = std::max(dmax, off[(size_t) r1] - off[(size_t) (g * 8)]);
+                    }
+                    const int smaxp = (flen + dmax + 3) & ~3;
+                    std::vector<double> gb((size_t) ng * smaxp * 8, 0.0);
+                    std::vector<int> go((size_t) ng);
+                    for (int g = 0; g < ng; g++) {
+                        const int o0 = off[(size_t) (g * 8)];
+                        go[(size_t) g] = o0;
+                        for (int r = 0; r < 8; r++) {
+                            const int rr = std::min(g * 8 + r, s.out_step - 1);
+                            const int dr = off[(size_t) rr] - o0;
+                            const double* rowp = s.bank.table.data() + (size_t) row[(size_t) rr] * flen;
+                            for (int i = 0; i < flen; i++) gb[((size_t) g * smaxp + dr + i) * 8 + r] = rowp[i];
+                        }
+                    }
+                    d.gbank_len = (int) gb.size();
+                    d.smaxp = smaxp;
+                    if (!cuda_ok(cudaMalloc(&d.gbank, gb.size() * sizeof(double)), "cudaMalloc(gbank)")) return nullptr;
+                    if (!cuda_ok(cudaMalloc(&d.goff, go.size() * sizeof(int)), "cudaMalloc(goff)")) return nullptr;
+                    cudaMemcpy(d.gbank, gb.data(), gb.size() * sizeof(double), cudaMemcpyHostToDevice);
+                    cudaMemcpy(d.goff, go.data(), go.size() * sizeof(int), cudaMemcpyHostToDevice);
+                    b->dev_bytes += gb.size() * sizeof(double);
+                }
+                d.bank_in_smem = (fused_smem_bytes(d.gbank_len) <= 220 * 1024) ? 1 : 0;
             }
         }
     }
@@ -628,6 +663,10 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.bank = fd.bank;
             p.bank_len = (int) f.bank.table.size();
             p.bank_in_smem = fd.bank_in_smem;
+            p.gbank = fd.gbank;
+            p.gbank_len = fd.gbank_len;
+            p.smaxp = fd.smaxp;
+            p.goff = fd.goff;
             p.in_step = f.in_step;
             p.out_step = f.out_step;
             p.phase_off = fd.phase_off;

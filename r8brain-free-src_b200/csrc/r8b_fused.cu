@@ -160,21 +160,14 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
     const int n_groups = (p.out_step + IR - 1) / IR;
     const int n_chunks = (int) ((c_last - c_first + 32 * IQ) / (32 * IQ));
     const int n_tasks = n_groups * n_chunks;
-    const int flen = p.flen;
+    const int smaxp = p.smaxp;
     for (int task = warp; task < n_tasks; task += FNT / 32) {
         const int grp = task % n_groups, chunk = task / n_groups;
         const int r0 = grp * IR;
-        int d[IR];
-        int br[IR]; // bank row offset biased by -d[r]: tap (s - d[r]) of phase r is bank[br[r] + s]
-        const int o0 = __ldg(&p.phase_off[r0]);
-#pragma unroll
-        for (int r = 0; r < IR; r++) {
-            const int rr = (r0 + r < p.out_step) ? r0 + r : p.out_step - 1;
-            d[r] = __ldg(&p.phase_off[rr]) - o0;
-            br[r] = __ldg(&p.phase_row[rr]) * flen - d[r];
-        }
-        const int dmax = d[IR - 1];
-        const int smax = dmax + flen;
+        const int o0 = __ldg(&p.goff[grp]);
+        // group bank: [smaxp][IR] coefficients, phase r's filter pre-shifted by its window offset and
+        // zero-padded, so the tap loop below has no predicates and one base address
+        const double* __restrict__ gb = bank + (long long) grp * smaxp * IR;
         int yo[IQ];
 #pragma unroll
         for (int q = 0; q < IQ; q++) {
@@ -184,7 +177,7 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
             const bool use_b = ws >= bsel;
             long long li = ws - (use_b ? yb0 : ya0);
             if (li < 0) li = 0; // edge-cycle phases this pair does not own: never stored
-            if (li > YMAX - smax) li = YMAX - smax;
+            if (li > YMAX - smaxp) li = YMAX - smaxp;
             yo[q] = (int) li + (PAD ? 0 : (use_b ? off_b : off_a));
             if (PAD) yo[q] |= use_b ? 0 : (1 << 30); // buffer select kept in bit 30 (layout applied per load)
         }
@@ -198,61 +191,20 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
         for (int r = 0; r < IR; r++)
 #pragma unroll
             for (int q = 0; q < IQ; q++) acc[r][q] = 0.0;
-        const int mid0 = dmax < flen ? dmax : flen, mid1 = dmax < flen ? flen : dmax;
-        int s = 0;
-#pragma unroll 1
-        for (; s < mid0; s++) { // ramp-up: phases with d[r] <= s
-            double yv[IQ];
-#pragma unroll
-            for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
-#pragma unroll
-            for (int r = 0; r < IR; r++)
-                if (d[r] <= s) {
-                    const double b = bank[br[r] + s];
-#pragma unroll
-                    for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
-                }
-        }
-        if (dmax < flen) {
 #pragma unroll 4
-            for (; s < mid1; s++) { // every phase active: no predicates
-                double yv[IQ];
-#pragma unroll
-                for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
-#pragma unroll
-                for (int r = 0; r < IR; r++) {
-                    const double b = bank[br[r] + s];
-#pragma unroll
-                    for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
-                }
-            }
-        } else {
-#pragma unroll 1
-            for (; s < mid1; s++) { // sparse case (d spans more than one filter length)
-                double yv[IQ];
-#pragma unroll
-                for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
-#pragma unroll
-                for (int r = 0; r < IR; r++)
-                    if ((unsigned) (s - d[r]) < (unsigned) flen) {
-                        const double b = bank[br[r] + s];
-#pragma unroll
-                        for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
-                    }
-            }
-        }
-#pragma unroll 1
-        for (; s < smax; s++) { // ramp-down: phases with s - d[r] < flen
+        for (int s = 0; s < smaxp; s++) { // smaxp is a multiple of 4
             double yv[IQ];
 #pragma unroll
             for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
 #pragma unroll
-            for (int r = 0; r < IR; r++)
-                if (s - d[r] < flen) {
-                    const double b = bank[br[r] + s];
+            for (int r = 0; r < IR; r += 2) {
+                const double2 b = *reinterpret_cast<const double2*>(gb + s * IR + r); // warp-uniform
 #pragma unroll
-                    for (int q = 0; q < IQ; q++) acc[r][q] = fma(b, yv[q], acc[r][q]);
+                for (int q = 0; q < IQ; q++) {
+                    acc[r][q] = fma(b.x, yv[q], acc[r][q]);
+                    acc[r + 1][q] = fma(b.y, yv[q], acc[r + 1][q]);
                 }
+            }
         }
         // each lane owns IR consecutive outputs per cycle (64 contiguous bytes)
         const bool linear = (dst.mask == -1);
@@ -331,7 +283,7 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     else if (tid < 128) twf[tid - 64] = __ldg(&p.tw[tid - 64]);
     __syncthreads();
     if (MODE == 0 && p.bank_in_smem)
-        for (int i = tid; i < p.bank_len; i += FNT) sbank[i] = __ldg(&p.bank[i]);
+        for (int i = tid; i < p.gbank_len; i += FNT) sbank[i] = __ldg(&p.gbank[i]);
 
     if (tid < 256) fwd_pass1_gather(bufA, twc, twf, src, ch, wa, wb, has_b, tid);
     __syncthreads();
@@ -416,10 +368,10 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
         const int off_a = 2 * FPL, off_b = 0; // tile a lives in bufB, tile b in bufA (in doubles)
         if (p.ysh == 31) {
             if (p.bank_in_smem) interp_whole<false, true>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, sbank, tid);
-            else interp_whole<false, false>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, p.bank, tid);
+            else interp_whole<false, false>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, p.gbank, tid);
         } else {
             if (p.bank_in_smem) interp_whole<true, true>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, sbank, tid);
-            else interp_whole<true, false>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, p.bank, tid);
+            else interp_whole<true, false>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, p.gbank, tid);
         }
     } else {
         // order-2 bank: output k of this call (k >= 0) sits at (p_k, fpos_k); find the pair's k range
@@ -485,7 +437,7 @@ int fused_max_span(int lg, int yl, int yr) { return 2 * (FM - 2 * lg) - yl - yr;
 void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
 {
     if (p.n_tiles <= 0 || n_ch <= 0) return;
-    const int smem = fused_smem_bytes(p.bank_in_smem ? p.bank_len : 0);
+    const int smem = fused_smem_bytes((p.mode == 0 && p.bank_in_smem) ? p.gbank_len : 0);
     static bool configured[16][2] = {};
     int dev = 0;
     cudaGetDevice(&dev);
