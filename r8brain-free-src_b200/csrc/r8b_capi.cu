@@ -75,7 +75,7 @@ void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec
                     std::vector<double2>& tw, double* nyq_gain)
 {
     const int M = 1 << fft_log2;
-    const int L = s.lp.half_len, U = s.up;
+    const int L = s.lp.half_len, U = (s.up > 2) ? 1 : s.up; // up = 3 runs on the zero-stuffed stream
     const long double two_pi = 6.283185307179586476925286766559005768L;
     std::vector<long double> cs((size_t) M), sn((size_t) M);
     for (int k = 0; k < M; k++) {
@@ -121,19 +121,20 @@ void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec
     switch (fft_log2) {
     case 10: fill_slot_order<1024>(nat, spec_slots); break;
     case 11: fill_slot_order<2048>(nat, spec_slots); break;
+    case 13: fill_slot_order<8192>(nat, spec_slots); break;
     default: fill_slot_order<4096>(nat, spec_slots); break;
     }
 }
 
-int choose_fft_log2(int lg)
+int choose_fft_log2(int lg, int max_log2)
 {
     if (const char* e = getenv("R8BGPU_FFT_LOG2")) {
         const int v = atoi(e);
-        if (v >= 10 && v <= 12 && (1 << v) - 2 * lg >= 64) return v;
+        if (v >= 10 && v <= max_log2 && (1 << v) - 2 * lg >= 64) return v;
     }
     int best = -1;
     double best_cost = 0.0;
-    for (int b = 10; b <= 12; b++) {
+    for (int b = 10; b <= max_log2; b++) {
         const int m = 1 << b;
         const int valid = m - 2 * lg;
         if (valid < 64) continue;
@@ -148,7 +149,7 @@ int choose_fft_log2(int lg)
 
 struct StageDev {
     // BLOCKCONV
-    int fft_log2 = 0, lg = 0;
+    int fft_log2 = 0, lg = 0, virt_up = 1;
     double nyq_gain = 0.0;
     double2* spec = nullptr;
     double2* tw = nullptr;
@@ -430,16 +431,17 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
             b->dev_bytes += ring_bytes;
         }
         if (s.kind == ST_BLOCKCONV) {
-            if (s.up > 2) {
-                set_err("batch_create: BlockConvolver up-factor 3 is not implemented yet");
-                return nullptr;
-            }
-            d.lg = (s.lp.half_len + s.up - 1) / s.up;
-            d.fft_log2 = choose_fft_log2(d.lg);
+            // up-factors other than 1 and 2 (the planner only makes 3) run as a 1x convolution over the
+            // zero-stuffed stream, exactly as the reference does
+            d.virt_up = (s.up > 2) ? s.up : 1;
+            const int up_eff = (s.up > 2) ? 1 : s.up;
+            d.lg = (s.lp.half_len + up_eff - 1) / up_eff;
+            d.fft_log2 = choose_fft_log2(d.lg, up_eff == 1 ? 13 : 12);
             if (s.block_exact) { // tiles == the reference's own blocks
                 d.lg = s.ref_prev_len - s.lp.half_len;
                 d.fft_log2 = s.lp.block_len_bits + 1;
-                if (d.fft_log2 < 10 || d.fft_log2 > 12) d.fft_log2 = -1;
+                // M = 8192 exists for 1x stages (single buffer); 2x stages stop at 4096
+                if (d.fft_log2 < 10 || d.fft_log2 > (up_eff == 1 ? 13 : 12)) d.fft_log2 = -1;
             }
             if (d.fused_with_next) d.fft_log2 = 12; // the fused kernel is built for M = 4096
             if (d.fft_log2 < 0) {
@@ -685,14 +687,16 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
         switch (s.kind) {
         case ST_BLOCKCONV: {
             BlockConvParams p;
-            p.up = s.up;
+            const int up_eff = d.virt_up > 1 ? 1 : s.up;
+            p.up = up_eff;
+            p.src_up = d.virt_up;
             p.down = s.down;
             p.lg = d.lg;
             p.fft_log2 = d.fft_log2;
             p.e0 = c.e0;
             p.e1 = c.e1;
-            p.m0 = (c.e0 * s.down) / s.up;               // floor; indices are >= 0
-            p.m1 = ((c.e1 - 1) * s.down) / s.up + 1;
+            p.m0 = (c.e0 * s.down) / up_eff;             // floor; indices are >= 0
+            p.m1 = ((c.e1 - 1) * s.down) / up_eff + 1;
             if (s.block_exact) {
                 // tile b = reference block b: owns positions [b*InputLen - L, (b+1)*InputLen - L)
                 const long long il = s.ref_input_len, L = s.lp.half_len;

@@ -144,9 +144,16 @@ __device__ __forceinline__ void fft_pass_inverse(double2* __restrict__ s,
 template <int M, int NT>
 __device__ __forceinline__ void fft_forward(double2* s, const double2* tw, int tid)
 {
-    constexpr int R1 = M / 256;
-    fft_pass_forward<M, M, R1, NT>(s, tw, tid);
-    __syncthreads();
+    if constexpr (M == 8192) { // 2 * 16 * 16 * 16
+        fft_pass_forward<M, M, 2, NT>(s, tw, tid);
+        __syncthreads();
+        fft_pass_forward<M, 4096, 16, NT>(s, tw, tid);
+        __syncthreads();
+    } else {
+        constexpr int R1 = M / 256;
+        fft_pass_forward<M, M, R1, NT>(s, tw, tid);
+        __syncthreads();
+    }
     fft_pass_forward<M, 256, 16, NT>(s, tw, tid);
     __syncthreads();
     fft_pass_forward<M, 16, 16, NT>(s, tw, tid);
@@ -156,26 +163,37 @@ __device__ __forceinline__ void fft_forward(double2* s, const double2* tw, int t
 template <int M, int NT>
 __device__ __forceinline__ void fft_inverse(double2* s, const double2* tw, int tid)
 {
-    constexpr int R1 = M / 256;
+    constexpr int R1 = (M == 8192) ? 2 : M / 256;
+    (void) R1;
     fft_pass_inverse<M, 16, 16, NT>(s, tw, tid);
     __syncthreads();
     fft_pass_inverse<M, 256, 16, NT>(s, tw, tid);
     __syncthreads();
-    fft_pass_inverse<M, M, R1, NT>(s, tw, tid);
-    __syncthreads();
+    if constexpr (M == 8192) {
+        fft_pass_inverse<M, 4096, 16, NT>(s, tw, tid);
+        __syncthreads();
+        fft_pass_inverse<M, M, 2, NT>(s, tw, tid);
+        __syncthreads();
+    } else {
+        fft_pass_inverse<M, M, R1, NT>(s, tw, tid);
+        __syncthreads();
+    }
 }
 
 // Frequency index k (0..M-1) <-> storage slot after fft_forward.
 //   k = q1 + R1*(q2 + 16*q3)  ->  slot = q1*256 + q2*16 + q3
+//   M = 8192 has one more (radix-2) leading digit: k = q0 + 2*(q1 + 16*(q2 + 16*q3)) -> slot = q0*4096 + q1*256 + q2*16 + q3
 template <int M>
 __host__ __device__ __forceinline__ constexpr int slot_of(int k)
 {
+    if (M == 8192) return (k % 2) * 4096 + ((k / 2) % 16) * 256 + ((k / 32) % 16) * 16 + (k / 512);
     constexpr int R1 = M / 256;
     return (k % R1) * 256 + ((k / R1) % 16) * 16 + (k / (R1 * 16));
 }
 template <int M>
 __host__ __device__ __forceinline__ constexpr int freq_of(int slot)
 {
+    if (M == 8192) return (slot / 4096) + 2 * (((slot / 256) % 16) + 16 * (((slot / 16) % 16) + 16 * (slot % 16)));
     constexpr int R1 = M / 256;
     return (slot / 256) + R1 * (((slot / 16) % 16) + 16 * (slot % 16));
 }

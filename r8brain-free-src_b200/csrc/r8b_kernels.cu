@@ -64,10 +64,22 @@ __global__ void __launch_bounds__(NT) k_blockconv(BlockConvParams p, SrcView src
     const long long mb = ma + p.adv;
     const long long wa = ma - p.lg, wb = mb - p.lg;
 
-    for (int n = tid; n < M; n += NT) {
-        const double xa = src_read(src, ch, wa + n);
-        const double xb = has_b ? src_read(src, ch, wb + n) : 0.0;
-        zbuf[fft_pad(n)] = make_double2(xa, xb);
+    if (p.src_up <= 1) {
+        for (int n = tid; n < M; n += NT) {
+            const double xa = src_read(src, ch, wa + n);
+            const double xb = has_b ? src_read(src, ch, wb + n) : 0.0;
+            zbuf[fft_pad(n)] = make_double2(xa, xb);
+        }
+    } else {
+        // Non-power-of-two up-factors (3x): the reference zero-stuffs in the time domain
+        // (copyUpsample, CDSPBlockConvolver.h:414-496); same here -- the tile is a window of the
+        // zero-stuffed stream, read through a virtual view of the source.
+        for (int n = tid; n < M; n += NT) {
+            const long long ua = wa + n, ub = wb + n;
+            const double xa = (ua >= 0 && ua % p.src_up == 0) ? src_read(src, ch, ua / p.src_up) : 0.0;
+            const double xb = (has_b && ub >= 0 && ub % p.src_up == 0) ? src_read(src, ch, ub / p.src_up) : 0.0;
+            zbuf[fft_pad(n)] = make_double2(xa, xb);
+        }
     }
     __syncthreads();
     fft_forward<M, NT>(zbuf, p.tw, tid);
@@ -175,6 +187,7 @@ void launch_blockconv(const BlockConvParams& p, const SrcView& src, const DstVie
         switch (p.fft_log2) {
         case 10: launch_bc_inst<1024, 1>(p, src, dst, n_ch, st); break;
         case 11: launch_bc_inst<2048, 1>(p, src, dst, n_ch, st); break;
+        case 13: launch_bc_inst<8192, 1>(p, src, dst, n_ch, st); break; // 1x stages only (one buffer)
         default: launch_bc_inst<4096, 1>(p, src, dst, n_ch, st); break;
         }
     } else {

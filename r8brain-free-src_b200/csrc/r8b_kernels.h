@@ -28,7 +28,8 @@ struct DstView {
 };
 
 struct BlockConvParams {
-    int up, down;
+    int up, down;          // up is 1 or 2 here; other up-factors run as up = 1 on a zero-stuffed view
+    int src_up;            // > 1: tile positions index the zero-stuffed stream x[t/src_up] (t % src_up == 0)
     int lg;                // half support of the polyphase filters, in input samples
     int fft_log2;          // log2(M)
     int adv;               // valid input-rate positions per tile (<= M - 2*lg)

@@ -55,6 +55,11 @@ CHAINS = [
     (48000.0, 16000.0),    # BlockConv 1/3
     (44100.0, 192000.0),   # BlockConv -> interp -> BlockConv -> HBUp (intermediate interpolation)
     (44100.0, 22050.5),    # fractional downsampling just above 2x
+    (44100.0, 132300.0),   # BlockConv 3/1 (time-domain zero-stuffing)
+    (32000.0, 48000.0),    # BlockConv 3/2 (reference-exact power-of-two decimation on a 3x stream)
+    (48000.0, 36000.0),    # BlockConv 3/4
+    (48000.0, 32000.0),    # BlockConv 2/3
+    (8000.0, 48000.0),     # BlockConv 3/1 -> HBUp (third-band taps)
 ]
 
 
@@ -72,6 +77,7 @@ def test_dsd_cascade_extfft(pkg, ref_e1):
 
 
 def test_hbdown_cascade(pkg, ref):
+    # (EXTFFT variant below)
     ys, yr = run_both(pkg, ref, 2822400.0, 44100.0, [65536] * 8, n_ch=2, max_in=65536)
     check(ys, yr)
 
@@ -167,7 +173,6 @@ import os  # noqa: E402
 
 _VEC = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz"))
 _NAMES = [str(n) for n in _VEC["names"]]
-_UP3 = {"up3_32000_48000", "up6_8000_48000"}  # BlockConvolver with UpFactor 3: SURVEY section 8(f), not built yet
 
 
 @pytest.mark.parametrize("name", _NAMES)
@@ -176,10 +181,6 @@ def test_gpu_matches_golden_fixture(pkg, name):
     lens = [int(v) for v in _VEC[name + "/lens"]]
     x = _VEC[name + "/x"]
     stride = int(p[5])
-    if name in _UP3:
-        with pytest.raises(pkg.R8bGpuError):
-            pkg.ResamplerBatch(1, p[0], p[1], max(lens), p[2], p[3], device=0, extfft=int(p[4]))
-        return
     rb = pkg.ResamplerBatch(2, p[0], p[1], max(lens), p[2], p[3], device=0, extfft=int(p[4]))
     pos, ys, counts = 0, [], []
     for l in lens:
@@ -225,3 +226,16 @@ def test_mirror_class_api(pkg, ref):
     assert m <= MAX_TOL and rr <= RMS_TOL
     same = pkg.CDSPResampler(48000.0, 48000.0, 64)
     assert np.array_equal(same.process(x[:64]), x[:64])
+
+
+def test_hbdown_cascade_extfft(pkg, ref_e1):
+    # R8B_EXTFFT=1 doubles the reference's block length: the 1/2 BlockConvolver needs 8192-point tiles
+    ys, yr = run_both(pkg, ref_e1, 2822400.0, 44100.0, [65536] * 8, n_ch=2, extfft=1, max_in=65536)
+    check(ys, yr)
+
+
+def test_long_filters(pkg, ref):
+    # narrow transition band => long kernels (K = 6817 at 0.5 %): exercises the largest FFT tiles
+    for src, dst, tb in [(96000.0, 48000.0, 1.0), (44100.0, 48000.0, 1.0), (48000.0, 44100.0, 3.0)]:
+        ys, yr = run_both(pkg, ref, src, dst, [8192] * 4, n_ch=1, tb=tb, max_in=8192)
+        check(ys, yr)
