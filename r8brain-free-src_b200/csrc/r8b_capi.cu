@@ -167,6 +167,7 @@ struct StageDev {
     int* goff = nullptr;
     int gbank_len = 0, smaxp = 0;
     int yl = 0, yr = 0, ysh = 31, span_max = 0, bank_in_smem = 0;
+    int casc_len = 0; // >= 2 on the first stage of a run of HBUP stages executed by k_hbup_cascade
 };
 
 } // namespace
@@ -422,6 +423,14 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 }
             }
         }
+        if (s.kind == ST_HBUP && !d.fused_into_prev && !getenv("R8BGPU_NO_FUSION")) {
+            size_t c = 1;
+            while (i + c < st.size() && st[i + c].kind == ST_HBUP && c < 6) c++;
+            if (c >= 2) {
+                d.casc_len = (int) c;
+                for (size_t k = 1; k < c; k++) b->dev[i + k].fused_into_prev = true;
+            }
+        }
         if (d.fused_into_prev) {
             d.ring_cap = 0; // the link stream lives only in shared memory
         } else {
@@ -599,7 +608,8 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
         const StageDev& d = b->dev[i];
         if (d.fused_into_prev) continue; // handled together with the previous stage
         const bool fused = d.fused_with_next;
-        if ((fused ? b->calls[i + 1].e1 <= b->calls[i + 1].e0 : c.e1 <= c.e0)) continue;
+        const size_t last = fused ? i + 1 : (d.casc_len >= 2 ? i + (size_t) d.casc_len - 1 : i); // stage whose output this launch produces
+        if (b->calls[last].e1 <= b->calls[last].e0) continue;
         SrcView src;
         src.ring = d.ring + (long long) ch0 * d.ring_cap;
         src.ring_stride = d.ring_cap;
@@ -615,7 +625,6 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
         }
         src.avail = c.n1;
         DstView dst;
-        const size_t last = fused ? i + 1 : i; // stage whose output this launch produces
         if (last + 1 == ns) {
             dst.ptr = d_out;
             dst.stride = (long long) out_stride;
@@ -633,7 +642,47 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             cudaEventCreate(&ev.b);
             cudaEventRecord(ev.a, st);
         }
-        if (fused) {
+        if (d.casc_len >= 2) {
+            const int cl = d.casc_len;
+            HbCascadeParams p;
+            memset(&p, 0, sizeof p);
+            p.n_stages = cl;
+            for (int k = 0; k < cl; k++) {
+                const StageDesc& h = P.stages[i + (size_t) k];
+                p.ntaps[k] = h.hb_taps;
+                for (int j = 0; j < h.hb_taps; j++) p.taps[k][j] = h.hb[(size_t) j];
+            }
+            p.e0 = b->calls[last].e0;
+            p.e1 = b->calls[last].e1;
+            // halos, from the last stage backwards (see k_hbup_cascade)
+            p.lo_off[cl] = 0;
+            p.hi_off[cl] = 0;
+            for (int k = cl - 1; k >= 0; k--) {
+                const int T = p.ntaps[k];
+                p.lo_off[k] = (p.lo_off[k + 1] + 1) / 2 + T - 1;
+                p.hi_off[k] = (p.hi_off[k + 1] >= 1 ? (p.hi_off[k + 1] - 1) / 2 : -1) + T + 1;
+            }
+            int halo = 0;
+            for (int k = 0; k < cl; k++) halo += p.lo_off[k] + p.hi_off[k] + 8;
+            int budget = 14336; // doubles of shared memory per CTA (2 CTAs per SM; measured best); buffers carry a 5/4 skew
+            if (const char* e = getenv("R8BGPU_HB_SMEM_DOUBLES")) budget = atoi(e);
+            int w = (((budget * 4) / 5 - halo) / ((1 << cl) - 1)) & ~31;
+            if (w > 1024) w = 1024;
+            if (w < 32) w = 32;
+            p.w = w;
+            int off = 0;
+            for (int k = 0; k < cl; k++) {
+                p.boff[k] = off + p.lo_off[k] * 0; // buffer k starts at its own lo bound
+                off += (((w << k) + p.lo_off[k] + p.hi_off[k] + 8) * 5 + 3) / 4 + 2; // + slack: threads work in quads; 5/4 skew
+                off = (off + 1) & ~1;
+            }
+            const int smem_bytes = off * (int) sizeof(double);
+            p.a0 = p.e0 >> cl;
+            const long long span = p.e1 - (p.a0 << cl);
+            p.n_tiles = (int) ((span + ((long long) w << cl) - 1) / ((long long) w << cl));
+            launch_hbup_cascade(p, smem_bytes, src, dst, nch, st);
+            b->launches++;
+        } else if (fused) {
             const StageDesc& f = P.stages[i + 1];
             const StageCall& fc = b->calls[i + 1];
             const StageDev& fd = b->dev[i + 1];

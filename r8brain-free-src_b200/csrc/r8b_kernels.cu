@@ -335,4 +335,147 @@ void launch_save_tail(const double* cur, long long cur_stride, long long cur_bas
     k_save_tail<<<grid, 256, 0, st>>>(cur, cur_stride, cur_base, n0, n1, ring, ring_stride, ring_mask);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused cascade of half-band 2x upsamplers (CDSPHBUpsampler chain of e.g. 44100 -> 2822400,
+// CDSPResampler.h:207-211): one read of the first stream, one write of the last; every
+// intermediate rate lives only in shared memory.  A CTA owns `w` samples of the cascade's input
+// stream s0 (plus the halo the taps reach back/forward through all stages) and produces the
+// corresponding w * 2^c samples of s_c.
+//   s_{k+1}[2n] = s_k[n];  s_{k+1}[2n+1] = sum_j f_k[j] * (s_k[n-j] + s_k[n+1+j]);  s_k[<0] = 0.
+__device__ __forceinline__ int hb_pad(int i) { return i + (i >> 2); }
+
+// One cascade stage for a CTA: every thread produces 4 consecutive input positions (8 outputs) from a
+// register window of 2T+3 samples -- 2T+3 shared-memory loads instead of 4*2T.  All indices are 32-bit
+// tile-local; buffers use the skewed layout i -> i + (i >> 2) so that threads 4 samples apart hit
+// different banks (lane stride 5 doubles).  Because (4q + o) >> 2 == q + (o >> 2), every address is
+// 5q (loads) / 10q (stores) plus a warp-uniform term.
+template <int T>
+__device__ __forceinline__ void hb_stage(const double* __restrict__ in, long long in_lo, const double* __restrict__ f,
+                                         long long L, long long H, double* __restrict__ out, bool last,
+                                         const HbCascadeParams& p, const DstView& dst, int ch, int tid)
+{
+    const long long n_lo = (L >= 0) ? L / 2 : -((-L + 1) / 2);               // floor(L/2)
+    const long long n_hi = (H - 1 >= 0) ? (H - 1) / 2 : -((-(H - 1) + 1) / 2); // floor((H-1)/2), inclusive
+    const int n_quads = (int) ((n_hi - n_lo) / 4) + 1;
+    const int c2 = (int) (n_lo - in_lo) - (T - 1); // window start of quad 0 in the input buffer
+    const int cj = (int) (2 * n_lo - L);           // local output index of quad 0's first value (0 or -1)
+    const int NL = (int) (H - L);
+    double fr[T];
+#pragma unroll
+    for (int j = 0; j < T; j++) fr[j] = f[j];
+    // last stage: clip to the call's output range, in local coordinates
+    int jl = 0, jh = NL;
+    if (last) {
+        if (p.e0 > L) jl = (int) (p.e0 - L);
+        if (p.e1 < H) jh = (int) (p.e1 - L);
+    }
+    const bool neg = (L < 0); // stream values at negative indices are zeros, not filter outputs
+    double* const obase = (last && dst.mask == -1) ? dst.ptr + (long long) ch * dst.stride + (L - dst.base) : nullptr;
+    const bool vec_ok = obase != nullptr && ((reinterpret_cast<unsigned long long>(obase) & 15) == 0) && cj == 0;
+    for (int q = tid; q < n_quads; q += 256) {
+        double w[2 * T + 3];
+#pragma unroll
+        for (int i = 0; i < 2 * T + 3; i++) {
+            const int o = c2 + i;
+            w[i] = in[5 * q + o + (o >> 2)];
+        }
+        double v[8];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            double od = fr[0] * (w[T + m] + w[T - 1 + m]);
+#pragma unroll
+            for (int j = 1; j < T; j++) od = fma(fr[j], w[T + m + j] + w[T - 1 + m - j], od);
+            v[2 * m] = w[T - 1 + m];
+            v[2 * m + 1] = od;
+        }
+        const int j0 = 8 * q + cj;
+        if (last) {
+            if (vec_ok && j0 >= jl && j0 + 8 <= jh) {
+#pragma unroll
+                for (int m = 0; m < 4; m++)
+                    *reinterpret_cast<double2*>(obase + j0 + 2 * m) = make_double2(v[2 * m], v[2 * m + 1]);
+            } else if (obase != nullptr) {
+#pragma unroll
+                for (int m = 0; m < 8; m++)
+                    if (j0 + m >= jl && j0 + m < jh) obase[j0 + m] = v[m];
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; m++)
+                    if (j0 + m >= jl && j0 + m < jh) dst_write(dst, ch, L + j0 + m, v[m]);
+            }
+        } else if (!neg && j0 >= 0 && j0 + 8 <= NL) {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int o = cj + m;
+                out[10 * q + o + (o >> 2)] = v[m];
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                if (j0 + m >= 0 && j0 + m < NL) out[hb_pad(j0 + m)] = (L + j0 + m < 0) ? 0.0 : v[m];
+        }
+    }
+}
+
+constexpr int HB_NT = 256;
+__global__ void __launch_bounds__(HB_NT, 3) k_hbup_cascade(HbCascadeParams p, SrcView src, DstView dst)
+{
+    extern __shared__ double hsm[];
+    const int tid = threadIdx.x;
+    const int ch = blockIdx.y;
+    const long long A = p.a0 + (long long) blockIdx.x * p.w; // tile = s0 positions [A, A + w)
+    const int c = p.n_stages;
+
+    // stage 0: gather the input segment
+    {
+        const long long lo = A - p.lo_off[0], hi = A + p.w + p.hi_off[0];
+        double* b0 = hsm + p.boff[0];
+        for (long long n = lo + tid; n < hi; n += HB_NT) b0[hb_pad((int) (n - lo))] = (n < 0) ? 0.0 : src_read(src, ch, n);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < c; k++) {
+        const double* __restrict__ in = hsm + p.boff[k];
+        const long long in_lo = (A << k) - p.lo_off[k];
+        const bool last = (k + 1 == c);
+        const long long L = last ? (A << c) : ((A << (k + 1)) - p.lo_off[k + 1]);
+        const long long H = last ? ((A + p.w) << c) : (((A + p.w) << (k + 1)) + p.hi_off[k + 1]);
+        double* out = last ? nullptr : hsm + p.boff[k + 1];
+        const double* __restrict__ f = p.taps[k];
+        switch (p.ntaps[k]) {
+        case 1: hb_stage<1>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 2: hb_stage<2>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 3: hb_stage<3>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 4: hb_stage<4>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 5: hb_stage<5>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 6: hb_stage<6>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 7: hb_stage<7>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 8: hb_stage<8>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 9: hb_stage<9>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 10: hb_stage<10>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 11: hb_stage<11>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 12: hb_stage<12>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 13: hb_stage<13>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        default: hb_stage<14>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        }
+        __syncthreads();
+    }
+}
+
+void launch_hbup_cascade(const HbCascadeParams& p, int smem_bytes, const SrcView& src, const DstView& dst,
+                         int n_ch, cudaStream_t st)
+{
+    if (p.n_tiles <= 0 || n_ch <= 0) return;
+    static bool configured[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !configured[dev]) {
+        cudaFuncSetAttribute(k_hbup_cascade, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        configured[dev] = true;
+    }
+    dim3 grid((unsigned) p.n_tiles, (unsigned) n_ch);
+    k_hbup_cascade<<<grid, HB_NT, smem_bytes, st>>>(p, src, dst);
+}
+
 } // namespace r8bgpu

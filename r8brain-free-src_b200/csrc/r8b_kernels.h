@@ -62,6 +62,21 @@ struct HbParams {
     double taps[14];
 };
 
+// Fused chain of up to 6 half-band 2x upsamplers (k_hbup_cascade).
+struct HbCascadeParams {
+    int n_stages;
+    int ntaps[6];
+    double taps[6][14];
+    long long e0, e1;      // output indices of the LAST stage to write
+    long long a0;          // first tile starts at this position of the cascade's input stream
+    int w;                 // tile width in input-stream samples
+    int n_tiles;
+    int lo_off[7], hi_off[7]; // stage-k stream range a tile needs: [2^k*A - lo_off[k], 2^k*(A+w) + hi_off[k])
+    int boff[7];           // offsets (doubles) of the per-stage buffers in dynamic shared memory
+};
+void launch_hbup_cascade(const HbCascadeParams& p, int smem_bytes, const SrcView& src, const DstView& dst,
+                         int n_ch, cudaStream_t st);
+
 // Fused 2x BlockConvolver + fractional interpolator (r8b_fused.cu).  Positions are indices of the
 // 2x-rate stream between the two stages.
 struct FusedParams {
