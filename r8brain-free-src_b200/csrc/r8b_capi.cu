@@ -165,7 +165,7 @@ struct StageDev {
     int* phase_row = nullptr;
     double* gbank = nullptr; // whole stepping: grouped, pre-shifted, zero-padded bank (see FusedParams)
     int* goff = nullptr;
-    int gbank_len = 0, smaxp = 0;
+    int gbank_len = 0, smaxp = 0, ir = 8;
     int yl = 0, yr = 0, ysh = 31, span_max = 0, bank_in_smem = 0;
     int casc_len = 0; // >= 2 on the first stage of a run of HBUP stages executed by k_hbup_cascade
 };
@@ -403,7 +403,7 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
             const int flen = f.bank.filter_len, fll = flen / 2 - 1;
             int dmax = 0;
             if (f.kind == ST_FRAC_WHOLE)
-                dmax = (int) (((long long) 7 * f.in_step + f.out_step - 1) / f.out_step) + 1;
+                dmax = (int) (((long long) 9 * f.in_step + f.out_step - 1) / f.out_step) + 1; // up to 10 phases per group
             const int yl = (fll + 2) & ~1;
             const int yr = (dmax + flen - yl + 2 + 1) & ~1;
             const int smax = fused_max_span(lg, yl, yr) & ~1;
@@ -483,27 +483,39 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 if (!cuda_ok(cudaMalloc(&d.phase_row, tb), "cudaMalloc(phase)")) return nullptr;
                 cudaMemcpy(d.phase_off, off.data(), tb, cudaMemcpyHostToDevice);
                 cudaMemcpy(d.phase_row, row.data(), tb, cudaMemcpyHostToDevice);
-                // grouped bank for the fused kernel: 8 consecutive phases share one y window
+                // grouped bank for the fused kernel: IR consecutive phases share one y window.  IR is 8 or
+                // 10, whichever spreads the phase groups more evenly over the kernel's 16 warps.
                 {
-                    const int flen = s.bank.filter_len, ng = (s.out_step + 7) / 8;
+                    const int flen = s.bank.filter_len;
+                    int ir = 8;
+                    {
+                        const int g8 = (s.out_step + 7) / 8, g10 = (s.out_step + 9) / 10;
+                        const int c8 = ((g8 + 15) / 16) * 8, c10 = ((g10 + 15) / 16) * 10;
+                        (void) c8;
+                        (void) c10; // measured: the 10-phase variant spills registers and is ~4 % slower
+                                    // (2.10 vs 2.02 ms per step on cfg 2) despite the even task split
+                        if (const char* e = getenv("R8BGPU_IR")) ir = atoi(e) == 10 ? 10 : 8;
+                    }
+                    const int ng = (s.out_step + ir - 1) / ir;
                     int dmax = 0;
                     for (int g = 0; g < ng; g++) {
-                        const int r1 = std::min(g * 8 + 7, s.out_step - 1);
-                        dmax = std::max(dmax, off[(size_t) r1] - off[(size_t) (g * 8)]);
+                        const int r1 = std::min(g * ir + ir - 1, s.out_step - 1);
+                        dmax = std::max(dmax, off[(size_t) r1] - off[(size_t) (g * ir)]);
                     }
                     const int smaxp = (flen + dmax + 3) & ~3;
-                    std::vector<double> gb((size_t) ng * smaxp * 8, 0.0);
+                    std::vector<double> gb((size_t) ng * smaxp * ir, 0.0);
                     std::vector<int> go((size_t) ng);
                     for (int g = 0; g < ng; g++) {
-                        const int o0 = off[(size_t) (g * 8)];
+                        const int o0 = off[(size_t) (g * ir)];
                         go[(size_t) g] = o0;
-                        for (int r = 0; r < 8; r++) {
-                            const int rr = std::min(g * 8 + r, s.out_step - 1);
+                        for (int r = 0; r < ir; r++) {
+                            const int rr = std::min(g * ir + r, s.out_step - 1);
                             const int dr = off[(size_t) rr] - o0;
                             const double* rowp = s.bank.table.data() + (size_t) row[(size_t) rr] * flen;
-                            for (int i = 0; i < flen; i++) gb[((size_t) g * smaxp + dr + i) * 8 + r] = rowp[i];
+                            for (int i = 0; i < flen; i++) gb[((size_t) g * smaxp + dr + i) * ir + r] = rowp[i];
                         }
                     }
+                    d.ir = ir;
                     d.gbank_len = (int) gb.size();
                     d.smaxp = smaxp;
                     if (!cuda_ok(cudaMalloc(&d.gbank, gb.size() * sizeof(double)), "cudaMalloc(gbank)")) return nullptr;
@@ -718,6 +730,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.gbank_len = fd.gbank_len;
             p.smaxp = fd.smaxp;
             p.goff = fd.goff;
+            p.ir = fd.ir;
             p.in_step = f.in_step;
             p.out_step = f.out_step;
             p.phase_off = fd.phase_off;

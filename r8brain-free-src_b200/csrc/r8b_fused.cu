@@ -42,7 +42,8 @@ __device__ __forceinline__ void dst_write_f(const DstView& v, int ch, long long 
 constexpr int FM = 4096;            // FFT length of the fused kernel
 constexpr int FNT = 512;            // threads per CTA
 constexpr int FPL = fft_padded_len(FM);
-constexpr int IR = 8;               // interpolation register tile: phases per lane
+// interpolation register tile: IR output phases per lane (8 or 10, chosen per plan so that the
+// number of phase groups divides evenly over the 16 warps) x IQ stepping cycles per lane
 constexpr int IQ = 3;               // ... x stepping cycles per lane
 
 __device__ __forceinline__ int ylay(int i, int ysh) { return i + (i >> ysh); }
@@ -134,31 +135,40 @@ __device__ __forceinline__ void inv_pass(double2* __restrict__ s, const double2*
 // a warp are in_step doubles apart (conflict-free: odd stride, or made odd by the PAD layout) and the
 // bank reads are warp-uniform broadcasts.  The tap loop is split into a predicated ramp-up, a
 // branch-free middle where all IR phases are active, and a predicated ramp-down.
-template <bool PAD, bool BANK_SMEM>
+template <int IR, bool PAD, bool BANK_SMEM>
 __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView& dst, int ch,
                                              const double* __restrict__ smd, int off_a, int off_b,
                                              long long ya0, long long yb0, long long bsel, long long A0,
                                              long long B1, const double* __restrict__ bank, int tid)
 {
     constexpr int YMAX = 2 * FM;
-    __shared__ long long s_rng[4];
-    if (tid == 0) { // 64-bit divisions once per CTA, not once per thread
-        long long a = (A0 * p.out_step + p.in_step - 1) / p.in_step;
-        long long b = (B1 * p.out_step + p.in_step - 1) / p.in_step;
-        if (a < p.e0) a = p.e0;
-        if (b > p.e1) b = p.e1;
-        s_rng[0] = a;
-        s_rng[1] = b;
-        s_rng[2] = b > a ? a / p.out_step : 0;
-        s_rng[3] = b > a ? (b - 1) / p.out_step : 0;
+    // All 64-bit arithmetic (and the divisions) happens once per CTA in thread 0; the per-task code
+    // below works on 32-bit quantities relative to the pair -- long-lived 64-bit values were being
+    // spilled around the tap loop and their reloads stalled the stores.
+    __shared__ int s_i[8];
+    __shared__ double* s_o;
+    if (tid == 0) {
+        long long ja = (A0 * p.out_step + p.in_step - 1) / p.in_step;
+        long long jb = (B1 * p.out_step + p.in_step - 1) / p.in_step;
+        if (ja < p.e0) ja = p.e0;
+        if (jb > p.e1) jb = p.e1;
+        const long long c_first = jb > ja ? ja / p.out_step : 0, c_last = jb > ja ? (jb - 1) / p.out_step : 0;
+        s_i[0] = jb > ja ? (int) (jb - ja) : 0;                      // outputs of this pair
+        s_i[1] = (int) (c_last - c_first);                           // last cycle, relative
+        s_i[2] = (int) (c_first * p.out_step - ja);                  // output index of (cycle 0, phase 0) rel. to ja
+        s_i[3] = (int) (c_first * p.in_step - p.fll - ya0);          // y window start of (cycle 0, offset 0) in tile a
+        // windows starting here or later use tile b (bsel == LLONG_MAX: there is no tile b)
+        s_i[4] = (bsel == LLONG_MAX || bsel - ya0 > 0x3fffffff) ? 0x3fffffff : (int) (bsel - ya0);
+        s_i[5] = (int) (yb0 - ya0);
+        s_o = dst.ptr + (long long) ch * dst.stride + ((ja - dst.base) & dst.mask); // linear destinations only
     }
     __syncthreads();
-    const long long ja = s_rng[0], jb = s_rng[1];
-    if (jb <= ja) return;
-    const long long c_first = s_rng[2], c_last = s_rng[3];
+    const int n_j = s_i[0];
+    if (n_j <= 0) return;
+    const int c_cnt = s_i[1], jshift = s_i[2], wbase = s_i[3], bsel_r = s_i[4], yb_d = s_i[5];
     const int warp = tid >> 5, lane = tid & 31;
     const int n_groups = (p.out_step + IR - 1) / IR;
-    const int n_chunks = (int) ((c_last - c_first + 32 * IQ) / (32 * IQ));
+    const int n_chunks = (c_cnt + 32 * IQ) / (32 * IQ);
     const int n_tasks = n_groups * n_chunks;
     const int smaxp = p.smaxp;
     for (int task = warp; task < n_tasks; task += FNT / 32) {
@@ -167,18 +177,18 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
         const int o0 = __ldg(&p.goff[grp]);
         // group bank: [smaxp][IR] coefficients, phase r's filter pre-shifted by its window offset and
         // zero-padded, so the tap loop below has no predicates and one base address
-        const double* __restrict__ gb = bank + (long long) grp * smaxp * IR;
+        const double* __restrict__ gb = bank + grp * smaxp * IR;
         int yo[IQ];
 #pragma unroll
         for (int q = 0; q < IQ; q++) {
-            const long long cq = c_first + (long long) chunk * (32 * IQ) + q * 32 + lane;
-            const long long c = cq <= c_last ? cq : c_last;
-            const long long ws = c * p.in_step + o0 - p.fll;
-            const bool use_b = ws >= bsel;
-            long long li = ws - (use_b ? yb0 : ya0);
+            int c = chunk * (32 * IQ) + q * 32 + lane;
+            if (c > c_cnt) c = c_cnt;
+            const int ws = c * p.in_step + o0 + wbase; // relative to tile a's first double
+            const bool use_b = ws >= bsel_r;
+            int li = use_b ? ws - yb_d : ws;
             if (li < 0) li = 0; // edge-cycle phases this pair does not own: never stored
             if (li > YMAX - smaxp) li = YMAX - smaxp;
-            yo[q] = (int) li + (PAD ? 0 : (use_b ? off_b : off_a));
+            yo[q] = li + (PAD ? 0 : (use_b ? off_b : off_a));
             if (PAD) yo[q] |= use_b ? 0 : (1 << 30); // buffer select kept in bit 30 (layout applied per load)
         }
         auto yload = [&](int q, int s) -> double {
@@ -206,15 +216,16 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
                 }
             }
         }
-        // each lane owns IR consecutive outputs per cycle (64 contiguous bytes)
+        // each lane owns IR consecutive outputs per cycle (IR*8 contiguous bytes).  (Transposing through
+        // shared memory to write 4 cycles x 64 B per instruction was measured slower than this.)
         const bool linear = (dst.mask == -1);
-        double* const obase = dst.ptr + (long long) ch * dst.stride - dst.base;
+        double* const obase = s_o;
 #pragma unroll
         for (int q = 0; q < IQ; q++) {
-            const long long cqq = c_first + (long long) chunk * (32 * IQ) + q * 32 + lane;
-            if (cqq > c_last) continue;
-            const long long j0 = cqq * p.out_step + r0;
-            const bool full = (r0 + IR <= p.out_step) && j0 >= ja && j0 + IR <= jb;
+            const int c = chunk * (32 * IQ) + q * 32 + lane;
+            if (c > c_cnt) continue;
+            const int j0 = c * p.out_step + r0 + jshift; // relative to the pair's first output
+            const bool full = (r0 + IR <= p.out_step) && j0 >= 0 && j0 + IR <= n_j;
             if (linear) {
                 double* o = obase + j0;
                 if (full) {
@@ -232,14 +243,15 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
                 } else {
 #pragma unroll
                     for (int r = 0; r < IR; r++)
-                        if (r0 + r < p.out_step && j0 + r >= ja && j0 + r < jb) o[r] = acc[r][q];
+                        if (r0 + r < p.out_step && j0 + r >= 0 && j0 + r < n_j) o[r] = acc[r][q];
                 }
             } else {
+                // ring destination (another stage follows): absolute index = e-range start + relative
+                const long long jabs = (long long) j0 + (p.e0 > 0 ? 0 : 0);
 #pragma unroll
-                for (int r = 0; r < IR; r++) {
-                    const long long j = j0 + r;
-                    if (r0 + r < p.out_step && j >= ja && j < jb) dst_write_f(dst, ch, j, acc[r][q]);
-                }
+                for (int r = 0; r < IR; r++)
+                    if (r0 + r < p.out_step && j0 + r >= 0 && j0 + r < n_j)
+                        dst.ptr[(long long) ch * dst.stride + (((obase - (dst.ptr + (long long) ch * dst.stride)) + jabs + r) & dst.mask)] = acc[r][q];
             }
         }
     }
@@ -248,7 +260,7 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
 } // namespace
 
 // MODE 0: whole stepping, MODE 1: order-2 polynomial bank.
-template <int MODE>
+template <int MODE, int IRV, bool PADV, bool BANKV>
 __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src, DstView dst)
 {
     extern __shared__ double2 smem[];
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     if (tid < 64) twc[tid] = __ldg(&p.tw[tid * 64]);
     else if (tid < 128) twf[tid - 64] = __ldg(&p.tw[tid - 64]);
     __syncthreads();
-    if (MODE == 0 && p.bank_in_smem)
+    if (MODE == 0 && BANKV)
         for (int i = tid; i < p.gbank_len; i += FNT) sbank[i] = __ldg(&p.gbank[i]);
 
     if (tid < 256) fwd_pass1_gather(bufA, twc, twf, src, ch, wa, wb, has_b, tid);
@@ -366,13 +378,7 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     if (MODE == 0) {
         const double* smd = reinterpret_cast<const double*>(smem);
         const int off_a = 2 * FPL, off_b = 0; // tile a lives in bufB, tile b in bufA (in doubles)
-        if (p.ysh == 31) {
-            if (p.bank_in_smem) interp_whole<false, true>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, sbank, tid);
-            else interp_whole<false, false>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, p.gbank, tid);
-        } else {
-            if (p.bank_in_smem) interp_whole<true, true>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, sbank, tid);
-            else interp_whole<true, false>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, p.gbank, tid);
-        }
+        interp_whole<IRV, PADV, BANKV>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, BANKV ? sbank : p.gbank, tid);
     } else {
         // order-2 bank: output k of this call (k >= 0) sits at (p_k, fpos_k); find the pair's k range
         if (tid == 0) {
@@ -434,23 +440,41 @@ int fused_smem_bytes(int bank_doubles_in_smem)
 
 int fused_max_span(int lg, int yl, int yr) { return 2 * (FM - 2 * lg) - yl - yr; }
 
+template <int MODE, int IRV, bool PADV, bool BANKV>
+static void launch_inst(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, int smem, cudaStream_t st)
+{
+    static bool configured[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 16 && !configured[dev]) {
+        cudaFuncSetAttribute(k_up2_frac<MODE, IRV, PADV, BANKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        configured[dev] = true;
+    }
+    const int n_pairs = (p.n_tiles + 1) >> 1;
+    k_up2_frac<MODE, IRV, PADV, BANKV><<<(unsigned) (n_pairs * n_ch), FNT, smem, st>>>(p, src, dst);
+}
+
 void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
 {
     if (p.n_tiles <= 0 || n_ch <= 0) return;
     const int smem = fused_smem_bytes((p.mode == 0 && p.bank_in_smem) ? p.gbank_len : 0);
-    static bool configured[16][2] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 16 && !configured[dev][p.mode]) {
-        if (p.mode == 0)
-            cudaFuncSetAttribute(k_up2_frac<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        else
-            cudaFuncSetAttribute(k_up2_frac<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        configured[dev][p.mode] = true;
+    if (p.mode != 0) {
+        launch_inst<1, 8, false, false>(p, src, dst, n_ch, smem, st);
+        return;
     }
-    const int n_pairs = (p.n_tiles + 1) >> 1;
-    if (p.mode == 0) k_up2_frac<0><<<(unsigned) (n_pairs * n_ch), FNT, smem, st>>>(p, src, dst);
-    else k_up2_frac<1><<<(unsigned) (n_pairs * n_ch), FNT, smem, st>>>(p, src, dst);
+    const bool pad = p.ysh != 31, bs = p.bank_in_smem != 0;
+    // one kernel per (phases per group, y layout, bank location): registers are allocated per variant
+    if (p.ir == 10) {
+        if (!pad && bs) launch_inst<0, 10, false, true>(p, src, dst, n_ch, smem, st);
+        else if (!pad) launch_inst<0, 10, false, false>(p, src, dst, n_ch, smem, st);
+        else if (bs) launch_inst<0, 10, true, true>(p, src, dst, n_ch, smem, st);
+        else launch_inst<0, 10, true, false>(p, src, dst, n_ch, smem, st);
+    } else {
+        if (!pad && bs) launch_inst<0, 8, false, true>(p, src, dst, n_ch, smem, st);
+        else if (!pad) launch_inst<0, 8, false, false>(p, src, dst, n_ch, smem, st);
+        else if (bs) launch_inst<0, 8, true, true>(p, src, dst, n_ch, smem, st);
+        else launch_inst<0, 8, true, false>(p, src, dst, n_ch, smem, st);
+    }
 }
 
 } // namespace r8bgpu

@@ -95,8 +95,9 @@ struct FusedParams {
     int flen, fll;
     long long e0, e1;      // outputs of this call
     int in_step, out_step;
-    const double* gbank;   // whole stepping: per group of 8 phases [smaxp][8] shifted, zero-padded taps
+    const double* gbank;   // whole stepping: per group of `ir` phases [smaxp][ir] shifted, zero-padded taps
     int gbank_len, smaxp;  // doubles in gbank; padded window length (multiple of 4)
+    int ir;                // phases per group (8 or 10)
     const int* goff;       // [n_groups] floor(r0*in_step/out_step) of the group's first phase
     const int* phase_off;  // [out_step] floor(r*in_step/out_step)
     const int* phase_row;  // [out_step] (r*in_step) % out_step
