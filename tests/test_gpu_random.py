@@ -1,0 +1,60 @@
+"""Randomised GPU parity sweep: many rate pairs (every planner branch), presets, transition bands and
+ragged block sequences against the compiled reference.  Seeded, so failures are reproducible."""
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+pytestmark = pytest.mark.gpu
+
+RATES = [8000.0, 11025.0, 16000.0, 22050.0, 32000.0, 44100.0, 48000.0, 64000.0, 88200.0, 96000.0, 176400.0,
+         192000.0, 352800.0, 384000.0]
+
+
+def _pairs(rng, n):
+    out = []
+    while len(out) < n:
+        a, b = rng.choice(RATES, 2, replace=False)
+        if rng.random() < 0.25:  # odd, non-whole-stepping ratios
+            b = float(b) + float(rng.integers(1, 50))
+        if a / b > 40 or b / a > 40:
+            continue
+        out.append((float(a), float(b)))
+    return out
+
+
+@pytest.mark.parametrize("seed", list(range(1, 11)))
+def test_random_rates_and_chunkings(pkg, ref, seed):
+    rng = np.random.default_rng(seed)
+    for src, dst in _pairs(rng, 6):
+        atten = float(rng.choice([pkg.ATTEN_16IR, pkg.ATTEN_16, pkg.ATTEN_24, 206.91]))
+        tb = float(rng.choice([1.5, 2.0, 3.0, 7.0, 20.0]))
+        max_in = int(rng.choice([512, 2048, 6000]))
+        # enough input to get past the start-up latency of deep decimation chains
+        n_calls = 8 if src <= 4 * dst else 40
+        lens = [int(v) for v in rng.integers(0, max_in + 1, n_calls)] + [max_in]
+        x = ou.white_noise(2, sum(lens), seed * 100 + 7)
+        try:
+            rb = pkg.ResamplerBatch(2, src, dst, max_in, tb, atten, device=0)
+        except pkg.R8bGpuError as e:
+            # only documented gaps may be refused (kernels longer than the largest tile)
+            assert "too long" in str(e), (src, dst, tb, atten, str(e))
+            continue
+        rs = [ref.Resampler(src, dst, max_in, tb, atten) for _ in range(2)]
+        pos = 0
+        ya, yb = [[], []], [[], []]
+        for l in lens:
+            y = rb.process(x[:, pos:pos + l])
+            for c in range(2):
+                r = rs[c].process(x[c, pos:pos + l])
+                assert len(r) == y.shape[1], (src, dst, tb, atten, l, len(r), y.shape[1])
+                ya[c].append(y[c])
+                yb[c].append(r)
+            pos += l
+        for c in range(2):
+            a, b = np.concatenate(ya[c]), np.concatenate(yb[c])
+            if len(b) == 0 or not np.any(b):
+                assert not np.any(a)
+                continue
+            m, r = ou.parity_metrics(a, b)
+            assert m <= 32 * ou.EPS and r <= 4 * ou.EPS, (src, dst, tb, atten, m / ou.EPS, r / ou.EPS)
