@@ -274,16 +274,20 @@ def main():
             for t in stage_info[i + 1:]:
                 tail *= (t["up"] / t["down"]) if t["name"] == "blockconv" else (2 if t["name"] == "hbup" else 0.5 if t["name"] == "hbdown" else 1.0)
             rate[i + 1] = (dst / src) / tail
-    dom_bytes = 8.0 * n_ch * BLOCK * (rate[dom] + rate[dom + 1])
+    kernels = batch.stage_kernels()  # (kernel name, plan stages covered) per plan stage
+    span = max(1, kernels[dom][1])
+    # a fused kernel reads the stream entering its first stage and writes the one leaving its last
+    dom_bytes = 8.0 * n_ch * BLOCK * (rate[dom] + rate[dom + span])
     dom_ms = st_times[dom][1] / max(1, st_times[dom][2])
     peak, peak_src = measured_peaks()
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     path_bytes_per_in = 8.0 * (1.0 + dst / src)
-    roofline = {"bound": "hbm", "kernel": "k_" + st_times[dom][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": kernels[dom][0], "plan_stages_covered": span, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
                 "kernel_share_of_step": st_times[dom][1] / tot_stage_ms,
-                "stage_ms_per_step": {("%d:%s" % (i, t[0])): t[1] / K for i, t in enumerate(st_times)},
+                "stage_ms_per_step": {("%d:%s:%s" % (i, t[0], kernels[i][0])): t[1] / K for i, t in enumerate(st_times)},
+                "traffic_source": None,
                 "path": {"algorithmic_bytes_per_in_sample": path_bytes_per_in,
                          "achieved": path_bytes_per_in * value * 1e6 / world / 1e9,
                          "frac": path_bytes_per_in * value * 1e6 / world / 1e9 / peak}}

@@ -132,6 +132,9 @@ R8BGPU_API unsigned long long r8bgpu_batch_kernel_launches(const r8bgpu_batch* b
  * accumulated milliseconds (and launch count) of one stage since timing was (re-)enabled. */
 R8BGPU_API int r8bgpu_batch_set_timing(r8bgpu_batch* batch, int enable);
 R8BGPU_API double r8bgpu_batch_stage_time_ms(r8bgpu_batch* batch, int stage, unsigned long long* launches);
+/* Name of the kernel that executes plan stage `stage`; returns the number of consecutive plan stages
+ * that kernel covers (0: the stage is folded into an earlier stage's kernel), < 0 on error. */
+R8BGPU_API int r8bgpu_batch_stage_kernel(const r8bgpu_batch* batch, int stage, char* name, int cap);
 /* Bytes of device memory held by the batch (state rings + tables + staging). */
 R8BGPU_API unsigned long long r8bgpu_batch_device_bytes(const r8bgpu_batch* batch);
 

@@ -65,6 +65,7 @@ _SYMBOLS = {
     "r8bgpu_batch_sync": (C.c_int, [C.c_void_p]),
     "r8bgpu_batch_kernel_launches": (C.c_ulonglong, [C.c_void_p]),
     "r8bgpu_batch_device_bytes": (C.c_ulonglong, [C.c_void_p]),
+    "r8bgpu_batch_stage_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
     "r8bgpu_batch_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "r8bgpu_batch_stage_time_ms": (C.c_double, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]),
     "r8bgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
@@ -212,6 +213,15 @@ class Batch:
     @property
     def device_bytes(self):
         return int(lib().r8bgpu_batch_device_bytes(self._h))
+
+    def stage_kernels(self):
+        """[(kernel_name, n_plan_stages_covered)] per plan stage."""
+        out = []
+        for i in range(len(self.plan.stages())):
+            buf = C.create_string_buffer(64)
+            n = lib().r8bgpu_batch_stage_kernel(self._h, i, buf, 64)
+            out.append((buf.value.decode(), n))
+        return out
 
     def set_timing(self, enable=True):
         lib().r8bgpu_batch_set_timing(self._h, int(bool(enable)))

@@ -579,6 +579,43 @@ double r8bgpu_batch_stage_time_ms(r8bgpu_batch* b, int stage, unsigned long long
     return b->stage_ms[(size_t) stage];
 }
 
+// Which kernel executes plan stage `stage`, and how many consecutive plan stages it covers
+// (0 = this stage is folded into the kernel of an earlier stage).
+int r8bgpu_batch_stage_kernel(const r8bgpu_batch* b, int stage, char* name, int cap)
+{
+    if (stage < 0 || stage >= (int) b->plan->stages.size()) {
+        set_err("stage_kernel: bad stage index");
+        return -1;
+    }
+    const StageDev& d = b->dev[(size_t) stage];
+    const StageDesc& s = b->plan->stages[(size_t) stage];
+    const char* nm = "";
+    int span = 1;
+    if (d.fused_into_prev) {
+        nm = "(fused)";
+        span = 0;
+    } else if (d.fused_with_next) {
+        nm = "k_up2_frac";
+        span = 2;
+    } else if (d.casc_len >= 2) {
+        nm = "k_hbup_cascade";
+        span = d.casc_len;
+    } else {
+        switch (s.kind) {
+        case ST_BLOCKCONV: nm = "k_blockconv"; break;
+        case ST_FRAC_WHOLE: nm = "k_frac_whole"; break;
+        case ST_FRAC_POLY: nm = "k_frac_poly"; break;
+        case ST_HBUP: nm = "k_hbup"; break;
+        default: nm = "k_hbdown"; break;
+        }
+    }
+    if (name != nullptr && cap > 0) {
+        strncpy(name, nm, (size_t) cap - 1);
+        name[cap - 1] = 0;
+    }
+    return span;
+}
+
 int r8bgpu_batch_set_stream(r8bgpu_batch* b, void* stream)
 {
     b->stream = (cudaStream_t) stream;
@@ -731,6 +768,12 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.smaxp = fd.smaxp;
             p.goff = fd.goff;
             p.ir = fd.ir;
+            {
+                // store staging area behind the bank, if shared memory allows (whole stepping, 8-phase groups)
+                const int used = fused_fixed_doubles() + (p.bank_in_smem ? ((p.gbank_len + 1) & ~1) : 0);
+                p.stage_off = (p.mode == 0 && p.ir == 8 && !getenv("R8BGPU_NO_STAGE") &&
+                               (used + fused_stage_doubles()) * 8 <= 224 * 1024) ? used : 0;
+            }
             p.in_step = f.in_step;
             p.out_step = f.out_step;
             p.phase_off = fd.phase_off;

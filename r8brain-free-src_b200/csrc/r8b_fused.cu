@@ -139,7 +139,7 @@ template <int IR, bool PAD, bool BANK_SMEM>
 __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView& dst, int ch,
                                              const double* __restrict__ smd, int off_a, int off_b,
                                              long long ya0, long long yb0, long long bsel, long long A0,
-                                             long long B1, const double* __restrict__ bank, int tid)
+                                             long long B1, const double* __restrict__ bank, double* stage, int tid)
 {
     constexpr int YMAX = 2 * FM;
     // All 64-bit arithmetic (and the divisions) happens once per CTA in thread 0; the per-task code
@@ -216,10 +216,48 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
                 }
             }
         }
-        // each lane owns IR consecutive outputs per cycle (IR*8 contiguous bytes).  (Transposing through
-        // shared memory to write 4 cycles x 64 B per instruction was measured slower than this.)
+        // Each lane owns IR consecutive outputs of ITS cycle (one 64-byte row; rows of neighbouring lanes
+        // are out_step samples apart).  Storing straight from registers makes every STG.128 touch 32
+        // different rows (lg_throttle was ~20 % of the kernel).  With a per-warp staging area the warp
+        // transposes 4x4 blocks of 16-byte chunks so that 4 adjacent lanes write one whole row: 8 rows x
+        // 64 B per instruction.  Row r lives at prow(r)*64 B with its chunks XOR-swizzled -- both the
+        // row-wise writes and the transposed reads are bank-conflict free.
         const bool linear = (dst.mask == -1);
         double* const obase = s_o;
+        if (linear && stage != nullptr && IR == 8) {
+            double* const stg = stage + warp * 256;
+            const int wrow = (lane ^ ((lane >> 2) & 1)) * 8, wsw = (lane >> 1) & 3;
+#pragma unroll
+            for (int q = 0; q < IQ; q++) {
+                const int cb = chunk * (32 * IQ) + q * 32; // cycle of lane 0
+                if (cb > c_cnt) break;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    *reinterpret_cast<double2*>(stg + wrow + 2 * (i ^ wsw)) = make_double2(acc[2 * i][q], acc[2 * i + 1][q]);
+                __syncwarp();
+                const int ci = lane & 3;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int R = (lane & ~3) + t;
+                    const double2 v = *reinterpret_cast<const double2*>(
+                        stg + (R ^ ((R >> 2) & 1)) * 8 + 2 * (ci ^ ((R >> 1) & 3)));
+                    const int c = cb + R;
+                    const int j = c * p.out_step + r0 + jshift + 2 * ci; // first of this lane's two outputs
+                    if (c > c_cnt) continue;
+                    double* o = obase + j;
+                    const bool in0 = (r0 + 2 * ci < p.out_step) && j >= 0 && j < n_j;
+                    const bool in1 = (r0 + 2 * ci + 1 < p.out_step) && j + 1 >= 0 && j + 1 < n_j;
+                    if (in0 && in1 && ((reinterpret_cast<unsigned long long>(o) & 15) == 0)) {
+                        *reinterpret_cast<double2*>(o) = v;
+                    } else {
+                        if (in0) o[0] = v.x;
+                        if (in1) o[1] = v.y;
+                    }
+                }
+                __syncwarp();
+            }
+            continue;
+        }
 #pragma unroll
         for (int q = 0; q < IQ; q++) {
             const int c = chunk * (32 * IQ) + q * 32 + lane;
@@ -246,12 +284,11 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
                         if (r0 + r < p.out_step && j0 + r >= 0 && j0 + r < n_j) o[r] = acc[r][q];
                 }
             } else {
-                // ring destination (another stage follows): absolute index = e-range start + relative
-                const long long jabs = (long long) j0 + (p.e0 > 0 ? 0 : 0);
+                // ring destination (another stage follows)
 #pragma unroll
                 for (int r = 0; r < IR; r++)
                     if (r0 + r < p.out_step && j0 + r >= 0 && j0 + r < n_j)
-                        dst.ptr[(long long) ch * dst.stride + (((obase - (dst.ptr + (long long) ch * dst.stride)) + jabs + r) & dst.mask)] = acc[r][q];
+                        dst.ptr[(long long) ch * dst.stride + (((obase - (dst.ptr + (long long) ch * dst.stride)) + (long long) j0 + r) & dst.mask)] = acc[r][q];
             }
         }
     }
@@ -378,7 +415,8 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     if (MODE == 0) {
         const double* smd = reinterpret_cast<const double*>(smem);
         const int off_a = 2 * FPL, off_b = 0; // tile a lives in bufB, tile b in bufA (in doubles)
-        interp_whole<IRV, PADV, BANKV>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, BANKV ? sbank : p.gbank, tid);
+        interp_whole<IRV, PADV, BANKV>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, BANKV ? sbank : p.gbank,
+                                       p.stage_off > 0 ? reinterpret_cast<double*>(smem) + p.stage_off : nullptr, tid);
     } else {
         // order-2 bank: output k of this call (k >= 0) sits at (p_k, fpos_k); find the pair's k range
         if (tid == 0) {
@@ -439,6 +477,8 @@ int fused_smem_bytes(int bank_doubles_in_smem)
 }
 
 int fused_max_span(int lg, int yl, int yr) { return 2 * (FM - 2 * lg) - yl - yr; }
+int fused_stage_doubles() { return (FNT / 32) * 256; }              // 32 rows x 8 doubles per warp
+int fused_fixed_doubles() { return 2 * (2 * FPL + 256 + 128); }     // buffers + twiddle tables
 
 template <int MODE, int IRV, bool PADV, bool BANKV>
 static void launch_inst(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, int smem, cudaStream_t st)
@@ -457,7 +497,8 @@ static void launch_inst(const FusedParams& p, const SrcView& src, const DstView&
 void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
 {
     if (p.n_tiles <= 0 || n_ch <= 0) return;
-    const int smem = fused_smem_bytes((p.mode == 0 && p.bank_in_smem) ? p.gbank_len : 0);
+    int smem = fused_smem_bytes((p.mode == 0 && p.bank_in_smem) ? p.gbank_len : 0);
+    if (p.mode == 0 && p.stage_off > 0) smem = (p.stage_off + fused_stage_doubles()) * (int) sizeof(double);
     if (p.mode != 0) {
         launch_inst<1, 8, false, false>(p, src, dst, n_ch, smem, st);
         return;

@@ -82,6 +82,7 @@ void launch_hbup_cascade(const HbCascadeParams& p, int smem_bytes, const SrcView
 struct FusedParams {
     int mode;              // 0 whole stepping, 1 order-2 bank
     int n_tiles;           // tiles of `span` owned positions each, processed in pairs
+    int stage_off;         // offset (doubles) of the store staging area in dynamic smem, 0 = none
     int span;              // even
     long long p_lo, p_hi;  // owned position range of this call [p_lo, p_hi), p_lo even
     int yl;                // left margin of a tile's valid range (>= fll, even)
@@ -109,6 +110,8 @@ struct FusedParams {
 };
 int fused_smem_bytes(int bank_doubles_in_smem);
 int fused_max_span(int lg, int yl, int yr);
+int fused_stage_doubles();
+int fused_fixed_doubles();
 void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st);
 
 int blockconv_smem_bytes(int fft_log2, int up);
