@@ -68,7 +68,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -281,13 +281,26 @@ def main():
     dom_ms = st_times[dom][1] / max(1, st_times[dom][2])
     peak, peak_src = measured_peaks()
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/), scaled to
+    # this launch's in-samples; null when no capture of this kernel/workload is on file
+    traffic, traffic_src = None, None
+    try:
+        for fn in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
+            if fn.endswith(".json") and "ncu_summary" in fn:
+                with open(os.path.join(ROOT, "profiles", fn)) as f:
+                    ps = json.load(f)
+                if kernels[dom][0] in ps.get("kernel", "") and ps.get("workload") == args.workload:
+                    traffic = ps["dram_bytes_per_in_sample"] * n_ch * BLOCK
+                    traffic_src = "profiles/" + fn
+    except Exception:
+        pass
     path_bytes_per_in = 8.0 * (1.0 + dst / src)
     roofline = {"bound": "hbm", "kernel": kernels[dom][0], "plan_stages_covered": span, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
                 "kernel_share_of_step": st_times[dom][1] / tot_stage_ms,
                 "stage_ms_per_step": {("%d:%s:%s" % (i, t[0], kernels[i][0])): t[1] / K for i, t in enumerate(st_times)},
-                "traffic_source": None,
+                "traffic_source": traffic_src,
                 "path": {"algorithmic_bytes_per_in_sample": path_bytes_per_in,
                          "achieved": path_bytes_per_in * value * 1e6 / world / 1e9,
                          "frac": path_bytes_per_in * value * 1e6 / world / 1e9 / peak}}
