@@ -202,10 +202,25 @@ struct r8bgpu_batch {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;
     int host_groups = 1;
     std::vector<cudaEvent_t> ev_h2d, ev_k;
+    unsigned long long* prof = nullptr; // R8BGPU_PROFILE: phase cycle counters of the fused kernel
+    unsigned long long prof_ctas = 0;
 
     ~r8bgpu_batch()
     {
         DeviceGuard g(device);
+        if (prof != nullptr) {
+            unsigned long long h[8] = {};
+            cudaDeviceSynchronize();
+            cudaMemcpy(h, prof, sizeof h, cudaMemcpyDeviceToHost);
+            static const char* nm[8] = {"gather+fwd1", "fwd2", "fwd3", "C(split*G)", "inv1", "inv2", "inv3+ystore", "interp"};
+            unsigned long long tot = 0;
+            for (int i = 0; i < 8; i++) tot += h[i];
+            fprintf(stderr, "[r8bgpu profile] k_up2_frac phases, mean clk per CTA over %llu CTAs:\n", prof_ctas);
+            for (int i = 0; i < 8; i++)
+                fprintf(stderr, "  %-12s %9.0f  (%4.1f %%)\n", nm[i], prof_ctas ? (double) h[i] / prof_ctas : 0.0,
+                        tot ? 100.0 * h[i] / tot : 0.0);
+            cudaFree(prof);
+        }
         for (auto& d : dev) {
             cudaFree(d.spec);
             cudaFree(d.tw);
@@ -786,6 +801,13 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.in_pos_shift = fc.in_pos_shift;
             p.fpos0 = fc.fpos0;
             p.p0 = fc.p0;
+            if (b->prof == nullptr && getenv("R8BGPU_PROFILE")) {
+                cudaMalloc(&b->prof, 8 * sizeof(unsigned long long));
+                cudaMemset(b->prof, 0, 8 * sizeof(unsigned long long));
+            }
+            p.prof = b->prof;
+            if (const char* e = getenv("R8BGPU_DEBUG")) p.debug = atoi(e);
+            if (b->prof) b->prof_ctas += (unsigned long long) ((p.n_tiles + 1) / 2) * nch;
             launch_up2_frac(p, src, dst, nch, st);
             b->launches++;
         } else

@@ -57,12 +57,9 @@ __device__ __forceinline__ double2 tw_split(const double2* __restrict__ twc, con
 }
 
 // forward pass 1 fused with the gather from global memory (radix 16, NCUR = M, D = 256)
-__device__ __forceinline__ void fwd_pass1_gather(double2* __restrict__ s, const double2* __restrict__ twc,
-                                                 const double2* __restrict__ twf,
-                                                 const SrcView& src, int ch, long long wa, long long wb,
-                                                 bool has_b, int r)
+__device__ __forceinline__ void gather_loads(double2 (&v)[16], const SrcView& src, int ch, long long wa, long long wb,
+                                             bool has_b, int r)
 {
-    double2 v[16];
     // Interior tiles lie completely inside the caller's block: plain coalesced loads.  Only the
     // first tiles of a call reach back into the history ring (or ahead of the available input).
     const bool fast = wa >= src.cur_base && wb + FM <= src.avail && has_b;
@@ -82,6 +79,11 @@ __device__ __forceinline__ void fwd_pass1_gather(double2* __restrict__ s, const 
             v[j].y = has_b ? src_read_f(src, ch, wb + n) : 0.0;
         }
     }
+}
+
+__device__ __forceinline__ void fwd_pass1_regs(double2 (&v)[16], double2* __restrict__ s, const double2* __restrict__ twc,
+                                               const double2* __restrict__ twf, int r)
+{
     Network<16, +1>::run(v);
 #pragma unroll
     for (int q = 0; q < 16; q++) {
@@ -201,8 +203,9 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
         for (int r = 0; r < IR; r++)
 #pragma unroll
             for (int q = 0; q < IQ; q++) acc[r][q] = 0.0;
+        const int s_end = (p.debug & 2) ? 0 : smaxp;
 #pragma unroll 4
-        for (int s = 0; s < smaxp; s++) { // smaxp is a multiple of 4
+        for (int s = 0; s < s_end; s++) { // smaxp is a multiple of 4
             double yv[IQ];
 #pragma unroll
             for (int q = 0; q < IQ; q++) yv[q] = yload(q, s);
@@ -224,6 +227,10 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
         // row-wise writes and the transposed reads are bank-conflict free.
         const bool linear = (dst.mask == -1);
         double* const obase = s_o;
+        if (p.debug & 1) {
+            if (acc[0][0] == 1.2345e300) obase[0] = acc[1][1]; // keep the loop alive
+            continue;
+        }
         if (linear && stage != nullptr && IR == 8) {
             double* const stg = stage + warp * 256;
             const int wrow = (lane ^ ((lane >> 2) & 1)) * 8, wsw = (lane >> 1) & 3;
@@ -326,53 +333,77 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     const long long wa = (A0 - p.yl) / 2 - p.lg;
     const long long wb = (B0 - p.yl) / 2 - p.lg;
 
+    // the input gather goes first (longest latency), the table loads ride behind it
+    double2 gv[16];
+    if (tid < 256) gather_loads(gv, src, ch, wa, wb, has_b, tid);
     // tables into shared memory
     for (int i = tid; i < 256; i += FNT) tw2[i] = __ldg(&p.tw[i * (FM / 256)]);
     if (tid < 64) twc[tid] = __ldg(&p.tw[tid * 64]);
     else if (tid < 128) twf[tid - 64] = __ldg(&p.tw[tid - 64]);
+    if (MODE == 0 && BANKV) {
+        // threads 256..511 are otherwise idle during the forward transform: they fetch the bank
+        for (int i = tid - 256; i >= 0 && i < p.gbank_len; i += 256) sbank[i] = __ldg(&p.gbank[i]);
+    }
     __syncthreads();
-    if (MODE == 0 && BANKV)
-        for (int i = tid; i < p.gbank_len; i += FNT) sbank[i] = __ldg(&p.gbank[i]);
 
-    if (tid < 256) fwd_pass1_gather(bufA, twc, twf, src, ch, wa, wb, has_b, tid);
+    // optional phase timing (R8BGPU_PROFILE=1): thread 0 accumulates clock64() deltas per phase
+    long long t_prev = p.prof ? clock64() : 0;
+#define R8B_TICK(i)                                                                  \
+    if (p.prof != nullptr && tid == 0) {                                             \
+        const long long t_now = clock64();                                           \
+        atomicAdd(&p.prof[i], (unsigned long long) (t_now - t_prev));                \
+        t_prev = t_now;                                                              \
+    }
+    if (tid < 256) fwd_pass1_regs(gv, bufA, twc, twf, tid);
     __syncthreads();
+    R8B_TICK(0)
     if (tid < 256) fwd_pass<256>(bufA, p.tw, tw2, tid);
     __syncthreads();
+    R8B_TICK(1)
     if (tid < 256) fwd_pass<16>(bufA, p.tw, tw2, tid);
     __syncthreads();
+    R8B_TICK(2)
 
-    // C. frequency pairs (all spectrum loads issued before the first use)
+    // C. frequency pairs.  Only slots whose frequency k <= M/2 start a pair; in slot order those are the
+    //    slots with low digit q3 < 8 (k = q1 + 16 q2 + 256 q3), plus k = M/2 (slot 8).  Thread t handles
+    //    slots 16*((t>>3) + 64u) + (t&7): runs of 8 consecutive double2 (conflict-free), no idle iterations,
+    //    and every spectrum value is fetched exactly once per CTA.
     {
-        constexpr int NC = FM / FNT;
+        constexpr int NC = FM / (2 * FNT);
         double2 g1[NC], g2[NC];
-        int s2v[NC];
+        int s1v[NC], s2v[NC];
 #pragma unroll
         for (int u = 0; u < NC; u++) {
-            const int s1 = tid + u * FNT;
+            const int s1 = 16 * ((tid >> 3) + 64 * u) + (tid & 7);
             const int k = freq_of<FM>(s1);
             const int s2 = slot_of<FM>((FM - k) & (FM - 1));
-            s2v[u] = (k > FM / 2) ? -1 : s2;
+            s1v[u] = s1;
+            s2v[u] = s2;
             g1[u] = __ldg(&p.spec[s1]);
             g2[u] = __ldg(&p.spec[s2]);
         }
-#pragma unroll
-        for (int u = 0; u < NC; u++) {
-            if (s2v[u] < 0) continue;
-            const int s1 = tid + u * FNT, s2 = s2v[u];
+        auto do_pair = [&](int s1, int s2, double2 ga, double2 gb) {
             const double2 z1 = bufA[fft_pad(s1)];
             const double2 z2 = bufA[fft_pad(s2)];
             // X_a[k] = z1 + conj z2 (the 1/2 lives in G); X_a[M-k] = conj X_a[k]
             const double2 xa = make_double2(z1.x + z2.x, z1.y - z2.y);
             const double2 xb = make_double2(z1.y + z2.y, z2.x - z1.x); // -i (z1 - conj z2)
-            bufB[fft_pad(s1)] = cmul<+1>(xa, g1[u]);
-            bufA[fft_pad(s1)] = cmul<+1>(xb, g1[u]);
+            bufB[fft_pad(s1)] = cmul<+1>(xa, ga);
+            bufA[fft_pad(s1)] = cmul<+1>(xb, ga);
             if (s2 != s1) {
-                bufB[fft_pad(s2)] = cmul<+1>(make_double2(xa.x, -xa.y), g2[u]);
-                bufA[fft_pad(s2)] = cmul<+1>(make_double2(xb.x, -xb.y), g2[u]);
+                bufB[fft_pad(s2)] = cmul<+1>(make_double2(xa.x, -xa.y), gb);
+                bufA[fft_pad(s2)] = cmul<+1>(make_double2(xb.x, -xb.y), gb);
             }
+        };
+#pragma unroll
+        for (int u = 0; u < NC; u++) do_pair(s1v[u], s2v[u], g1[u], g2[u]);
+        if (tid == 0) { // k = M/2 pairs with itself
+            const int sh = slot_of<FM>(FM / 2);
+            do_pair(sh, sh, __ldg(&p.spec[sh]), __ldg(&p.spec[sh]));
         }
     }
     __syncthreads();
+    R8B_TICK(3)
 
     // D. two inverse transforms side by side
     {
@@ -380,8 +411,10 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
         const int g = tid & 255;
         inv_pass<16>(buf, tw2, g);
         __syncthreads();
+        R8B_TICK(4)
         inv_pass<256>(buf, tw2, g);
         __syncthreads();
+        R8B_TICK(5)
         // last pass: NCUR = M, D = 256, twiddle W_M^(r q) conj; results leave in y layout
         double2 v[16];
 #pragma unroll
@@ -400,11 +433,16 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
             double2 x = v[bitrev<16>(j)];
             const long long t0 = 2 * (w + e);    // absolute 2x-rate index of x.x
             if (t0 < 0) x = make_double2(0.0, 0.0); // the reference's interpolator starts from silence
-            yb[ylay(2 * e, p.ysh)] = x.x;
-            yb[ylay(2 * e + 1, p.ysh)] = x.y;
+            if (!PADV) {
+                reinterpret_cast<double2*>(yb)[e] = x; // plain layout: one 128-bit store
+            } else {
+                yb[ylay(2 * e, p.ysh)] = x.x;
+                yb[ylay(2 * e + 1, p.ysh)] = x.y;
+            }
         }
     }
     __syncthreads();
+    R8B_TICK(6)
 
     const double* ya = reinterpret_cast<const double*>(bufB);
     const double* ybuf_b = reinterpret_cast<const double*>(bufA);
@@ -469,6 +507,11 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
             dst_write_f(dst, ch, p.e0 + k, acc);
         }
     }
+    if (p.prof != nullptr) {
+        __syncthreads();
+        R8B_TICK(7)
+    }
+#undef R8B_TICK
 }
 
 int fused_smem_bytes(int bank_doubles_in_smem)
