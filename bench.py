@@ -199,7 +199,7 @@ def main():
 
     plan = pkg.Plan(src, dst, BLOCK, tb, atten, extfft=extfft)
     batch = pkg.Batch(plan, n_ch, local_rank)
-    cap = (plan.max_out_len + 3) // 4 * 4  # rows start 32-byte aligned
+    cap = (plan.max_out_len + 7) // 8 * 8  # rows start 64-byte aligned
     # Two distinct input blocks alternate so that no step re-reads a block that could sit in L2.
     xs = [torch.from_numpy(synth_block(n_ch, BLOCK, 1000 + 17 * rank + i)).to(dev) for i in range(2)]
     out = torch.empty((n_ch, cap), dtype=torch.float64, device=dev)

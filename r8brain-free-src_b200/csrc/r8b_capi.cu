@@ -165,7 +165,7 @@ struct StageDev {
     int* phase_row = nullptr;
     double* gbank = nullptr; // whole stepping: grouped, pre-shifted, zero-padded bank (see FusedParams)
     int* goff = nullptr;
-    int gbank_len = 0, smaxp = 0, ir = 8;
+    int gbank_len = 0, gbank_smem_len = 0, smaxp = 0, ir = 8;
     int yl = 0, yr = 0, ysh = 31, span_max = 0, bank_in_smem = 0;
     int casc_len = 0; // >= 2 on the first stage of a run of HBUP stages executed by k_hbup_cascade
 };
@@ -512,24 +512,25 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                         if (const char* e = getenv("R8BGPU_IR")) ir = atoi(e) == 10 ? 10 : 8;
                     }
                     const int ng = (s.out_step + ir - 1) / ir;
+                    const int os = s.out_step;
+                    // window offset of "phase" pr >= 0 counted from cycle 0 (pr >= os continues in later cycles)
+                    auto offx = [&](int pr) { return off[(size_t) (pr % os)] + (pr / os) * s.in_step; };
                     int dmax = 0;
-                    for (int g = 0; g < ng; g++) {
-                        const int r1 = std::min(g * ir + ir - 1, s.out_step - 1);
-                        dmax = std::max(dmax, off[(size_t) r1] - off[(size_t) (g * ir)]);
-                    }
+                    for (int r0 = 0; r0 < os; r0++) dmax = std::max(dmax, offx(r0 + ir - 1) - offx(r0));
                     const int smaxp = (flen + dmax + 3) & ~3;
-                    std::vector<double> gb((size_t) ng * smaxp * ir, 0.0);
-                    std::vector<int> go((size_t) ng);
-                    for (int g = 0; g < ng; g++) {
-                        const int o0 = off[(size_t) (g * ir)];
-                        go[(size_t) g] = o0;
+                    // one entry per possible first phase r0: lets a call start its groups at e0 mod 8
+                    std::vector<double> gb((size_t) os * smaxp * ir, 0.0);
+                    std::vector<int> go((size_t) os);
+                    for (int r0 = 0; r0 < os; r0++) {
+                        go[(size_t) r0] = off[(size_t) r0];
                         for (int r = 0; r < ir; r++) {
-                            const int rr = std::min(g * ir + r, s.out_step - 1);
-                            const int dr = off[(size_t) rr] - o0;
-                            const double* rowp = s.bank.table.data() + (size_t) row[(size_t) rr] * flen;
-                            for (int i = 0; i < flen; i++) gb[((size_t) g * smaxp + dr + i) * ir + r] = rowp[i];
+                            const int pr = r0 + r;
+                            const int dr = offx(pr) - offx(r0);
+                            const double* rowp = s.bank.table.data() + (size_t) row[(size_t) (pr % os)] * flen;
+                            for (int i = 0; i < flen; i++) gb[((size_t) r0 * smaxp + dr + i) * ir + r] = rowp[i];
                         }
                     }
+                    d.gbank_smem_len = ng * smaxp * ir;
                     d.ir = ir;
                     d.gbank_len = (int) gb.size();
                     d.smaxp = smaxp;
@@ -539,7 +540,7 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                     cudaMemcpy(d.goff, go.data(), go.size() * sizeof(int), cudaMemcpyHostToDevice);
                     b->dev_bytes += gb.size() * sizeof(double);
                 }
-                d.bank_in_smem = (fused_smem_bytes(d.gbank_len) <= 220 * 1024) ? 1 : 0;
+                d.bank_in_smem = (fused_smem_bytes(d.gbank_smem_len) <= 220 * 1024) ? 1 : 0;
             }
         }
     }
@@ -783,9 +784,12 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.smaxp = fd.smaxp;
             p.goff = fd.goff;
             p.ir = fd.ir;
+            p.gbank_smem_len = fd.gbank_smem_len;
+            p.wrap = (p.mode == 0 && f.out_step % 8 == 0 && !getenv("R8BGPU_NO_ALIGN")) ? 1 : 0;
+            p.delta = p.wrap ? (int) (fc.e0 & 7) : 0;
             {
                 // store staging area behind the bank, if shared memory allows (whole stepping, 8-phase groups)
-                const int used = fused_fixed_doubles() + (p.bank_in_smem ? ((p.gbank_len + 1) & ~1) : 0);
+                const int used = fused_fixed_doubles() + (p.bank_in_smem ? ((p.gbank_smem_len + 1) & ~1) : 0);
                 p.stage_off = (p.mode == 0 && p.ir == 8 && !getenv("R8BGPU_NO_STAGE") &&
                                (used + fused_stage_doubles()) * 8 <= 224 * 1024) ? used : 0;
             }

@@ -132,6 +132,29 @@ __device__ __forceinline__ void inv_pass(double2* __restrict__ s, const double2*
 }
 
 
+// Pair-level bookkeeping for the whole-stepping interpolation, done by ONE thread at kernel start (it
+// depends only on the launch parameters, so its 64-bit divisions hide behind the input gather).  Everything the
+// per-task code needs afterwards is 32-bit and relative to the pair.  With delta = e0 mod 8 (out_step % 8 == 0)
+// the phase groups are shifted so that every 8-phase row starts on a 64-byte boundary of the caller's buffer.
+__device__ __forceinline__ void interp_prepare(const FusedParams& p, const DstView& dst, int ch, long long ya0,
+                                               long long yb0, long long bsel, long long A0, long long B1, int* s_i,
+                                               double** s_op)
+{
+    long long ja = (A0 * p.out_step + p.in_step - 1) / p.in_step;
+    long long jb = (B1 * p.out_step + p.in_step - 1) / p.in_step;
+    if (ja < p.e0) ja = p.e0;
+    if (jb > p.e1) jb = p.e1;
+    const long long ad = ja - p.delta, bd = jb - 1 - p.delta; // floor divisions (ad may be slightly negative)
+    const long long c_first = ad >= 0 ? ad / p.out_step : -1, c_last = bd >= 0 ? bd / p.out_step : -1;
+    s_i[0] = jb > ja ? (int) (jb - ja) : 0;                               // outputs of this pair
+    s_i[1] = (int) (c_last - c_first);                                    // last (shifted) cycle, relative
+    s_i[2] = (int) (c_first * p.out_step - ja);                           // output index of (cycle 0, phase 0) rel. to ja
+    s_i[3] = (int) (c_first * p.in_step - p.fll - ya0);                   // y window start of (cycle 0, offset 0) in tile a
+    s_i[4] = (bsel == LLONG_MAX || bsel - ya0 > 0x3fffffff) ? 0x3fffffff : (int) (bsel - ya0);
+    s_i[5] = (int) (yb0 - ya0);
+    *s_op = dst.ptr + (long long) ch * dst.stride + ((ja - dst.base) & dst.mask);
+}
+
 // Whole-stepping interpolation of one tile pair out of shared memory.  Task = (group of IR
 // consecutive output phases) x (chunk of 32*IQ stepping cycles); lane = cycle, so the y reads of
 // a warp are in_step doubles apart (conflict-free: odd stride, or made odd by the PAD layout) and the
@@ -141,30 +164,13 @@ template <int IR, bool PAD, bool BANK_SMEM>
 __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView& dst, int ch,
                                              const double* __restrict__ smd, int off_a, int off_b,
                                              long long ya0, long long yb0, long long bsel, long long A0,
-                                             long long B1, const double* __restrict__ bank, double* stage, int tid)
+                                             long long B1, const double* __restrict__ bank, double* stage,
+                                             const int* __restrict__ s_i, double* const* s_op,
+                                             const int* __restrict__ s_goff, int tid)
 {
     constexpr int YMAX = 2 * FM;
-    // All 64-bit arithmetic (and the divisions) happens once per CTA in thread 0; the per-task code
-    // below works on 32-bit quantities relative to the pair -- long-lived 64-bit values were being
-    // spilled around the tap loop and their reloads stalled the stores.
-    __shared__ int s_i[8];
-    __shared__ double* s_o;
-    if (tid == 0) {
-        long long ja = (A0 * p.out_step + p.in_step - 1) / p.in_step;
-        long long jb = (B1 * p.out_step + p.in_step - 1) / p.in_step;
-        if (ja < p.e0) ja = p.e0;
-        if (jb > p.e1) jb = p.e1;
-        const long long c_first = jb > ja ? ja / p.out_step : 0, c_last = jb > ja ? (jb - 1) / p.out_step : 0;
-        s_i[0] = jb > ja ? (int) (jb - ja) : 0;                      // outputs of this pair
-        s_i[1] = (int) (c_last - c_first);                           // last cycle, relative
-        s_i[2] = (int) (c_first * p.out_step - ja);                  // output index of (cycle 0, phase 0) rel. to ja
-        s_i[3] = (int) (c_first * p.in_step - p.fll - ya0);          // y window start of (cycle 0, offset 0) in tile a
-        // windows starting here or later use tile b (bsel == LLONG_MAX: there is no tile b)
-        s_i[4] = (bsel == LLONG_MAX || bsel - ya0 > 0x3fffffff) ? 0x3fffffff : (int) (bsel - ya0);
-        s_i[5] = (int) (yb0 - ya0);
-        s_o = dst.ptr + (long long) ch * dst.stride + ((ja - dst.base) & dst.mask); // linear destinations only
-    }
-    __syncthreads();
+    (void) ya0; (void) yb0; (void) bsel; (void) A0; (void) B1;
+    double* const s_o = *s_op;
     const int n_j = s_i[0];
     if (n_j <= 0) return;
     const int c_cnt = s_i[1], jshift = s_i[2], wbase = s_i[3], bsel_r = s_i[4], yb_d = s_i[5];
@@ -175,11 +181,11 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
     const int smaxp = p.smaxp;
     for (int task = warp; task < n_tasks; task += FNT / 32) {
         const int grp = task % n_groups, chunk = task / n_groups;
-        const int r0 = grp * IR;
-        const int o0 = __ldg(&p.goff[grp]);
+        const int r0 = p.delta + grp * IR; // first phase of the group (phases past out_step wrap into the next cycle)
+        const int o0 = s_goff[grp];
         // group bank: [smaxp][IR] coefficients, phase r's filter pre-shifted by its window offset and
         // zero-padded, so the tap loop below has no predicates and one base address
-        const double* __restrict__ gb = bank + grp * smaxp * IR;
+        const double* __restrict__ gb = bank + (BANK_SMEM ? grp : r0) * smaxp * IR;
         int yo[IQ];
 #pragma unroll
         for (int q = 0; q < IQ; q++) {
@@ -252,8 +258,8 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
                     const int j = c * p.out_step + r0 + jshift + 2 * ci; // first of this lane's two outputs
                     if (c > c_cnt) continue;
                     double* o = obase + j;
-                    const bool in0 = (r0 + 2 * ci < p.out_step) && j >= 0 && j < n_j;
-                    const bool in1 = (r0 + 2 * ci + 1 < p.out_step) && j + 1 >= 0 && j + 1 < n_j;
+                    const bool in0 = (p.wrap || r0 + 2 * ci < p.out_step) && j >= 0 && j < n_j;
+                    const bool in1 = (p.wrap || r0 + 2 * ci + 1 < p.out_step) && j + 1 >= 0 && j + 1 < n_j;
                     if (in0 && in1 && ((reinterpret_cast<unsigned long long>(o) & 15) == 0)) {
                         *reinterpret_cast<double2*>(o) = v;
                     } else {
@@ -270,7 +276,7 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
             const int c = chunk * (32 * IQ) + q * 32 + lane;
             if (c > c_cnt) continue;
             const int j0 = c * p.out_step + r0 + jshift; // relative to the pair's first output
-            const bool full = (r0 + IR <= p.out_step) && j0 >= 0 && j0 + IR <= n_j;
+            const bool full = (p.wrap || r0 + IR <= p.out_step) && j0 >= 0 && j0 + IR <= n_j;
             if (linear) {
                 double* o = obase + j0;
                 if (full) {
@@ -288,13 +294,13 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
                 } else {
 #pragma unroll
                     for (int r = 0; r < IR; r++)
-                        if (r0 + r < p.out_step && j0 + r >= 0 && j0 + r < n_j) o[r] = acc[r][q];
+                        if ((p.wrap || r0 + r < p.out_step) && j0 + r >= 0 && j0 + r < n_j) o[r] = acc[r][q];
                 }
             } else {
                 // ring destination (another stage follows)
 #pragma unroll
                 for (int r = 0; r < IR; r++)
-                    if (r0 + r < p.out_step && j0 + r >= 0 && j0 + r < n_j)
+                    if ((p.wrap || r0 + r < p.out_step) && j0 + r >= 0 && j0 + r < n_j)
                         dst.ptr[(long long) ch * dst.stride + (((obase - (dst.ptr + (long long) ch * dst.stride)) + (long long) j0 + r) & dst.mask)] = acc[r][q];
             }
         }
@@ -315,6 +321,9 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     double2* twf = twc + 64;           // W_M^b, b < 64
     double* sbank = reinterpret_cast<double*>(twf + 64); // whole-step bank (if it fits)
     __shared__ int s_j[2];
+    __shared__ int s_i[8];
+    __shared__ double* s_o;
+    __shared__ int s_goff[192];
 
     const int tid = threadIdx.x;
     const int n_pairs = (p.n_tiles + 1) >> 1;
@@ -340,9 +349,21 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     for (int i = tid; i < 256; i += FNT) tw2[i] = __ldg(&p.tw[i * (FM / 256)]);
     if (tid < 64) twc[tid] = __ldg(&p.tw[tid * 64]);
     else if (tid < 128) twf[tid - 64] = __ldg(&p.tw[tid - 64]);
-    if (MODE == 0 && BANKV) {
-        // threads 256..511 are otherwise idle during the forward transform: they fetch the bank
-        for (int i = tid - 256; i >= 0 && i < p.gbank_len; i += 256) sbank[i] = __ldg(&p.gbank[i]);
+    if (MODE == 0) {
+        const int n_groups = (p.out_step + IRV - 1) / IRV, esz = p.smaxp * IRV;
+        if (BANKV) {
+            // threads 256..511 are otherwise idle during the forward transform: they fetch the bank entries of
+            // this call's phase groups (first phases delta, delta+8, ...) into consecutive slots
+            for (int i = tid - 256; i >= 0 && i < n_groups * esz; i += 256) {
+                const int g = i / esz;
+                sbank[i] = __ldg(&p.gbank[(long long) (p.delta + g * IRV) * esz + (i - g * esz)]);
+            }
+        }
+        if (tid >= 256 && tid - 256 < n_groups) s_goff[tid - 256] = __ldg(&p.goff[p.delta + (tid - 256) * IRV]);
+        if (tid == 511) {
+            const long long bsel0 = has_b ? B0 - p.yl : LLONG_MAX;
+            interp_prepare(p, dst, ch, 2 * wa, 2 * wb, bsel0, A0, B1, s_i, &s_o);
+        }
     }
     __syncthreads();
 
@@ -454,7 +475,8 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
         const double* smd = reinterpret_cast<const double*>(smem);
         const int off_a = 2 * FPL, off_b = 0; // tile a lives in bufB, tile b in bufA (in doubles)
         interp_whole<IRV, PADV, BANKV>(p, dst, ch, smd, off_a, off_b, ya0, yb0, bsel, A0, B1, BANKV ? sbank : p.gbank,
-                                       p.stage_off > 0 ? reinterpret_cast<double*>(smem) + p.stage_off : nullptr, tid);
+                                       p.stage_off > 0 ? reinterpret_cast<double*>(smem) + p.stage_off : nullptr, s_i, &s_o,
+                                       s_goff, tid);
     } else {
         // order-2 bank: output k of this call (k >= 0) sits at (p_k, fpos_k); find the pair's k range
         if (tid == 0) {
@@ -540,7 +562,7 @@ static void launch_inst(const FusedParams& p, const SrcView& src, const DstView&
 void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
 {
     if (p.n_tiles <= 0 || n_ch <= 0) return;
-    int smem = fused_smem_bytes((p.mode == 0 && p.bank_in_smem) ? p.gbank_len : 0);
+    int smem = fused_smem_bytes((p.mode == 0 && p.bank_in_smem) ? p.gbank_smem_len : 0);
     if (p.mode == 0 && p.stage_off > 0) smem = (p.stage_off + fused_stage_doubles()) * (int) sizeof(double);
     if (p.mode != 0) {
         launch_inst<1, 8, false, false>(p, src, dst, n_ch, smem, st);

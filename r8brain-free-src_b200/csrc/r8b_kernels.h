@@ -98,10 +98,13 @@ struct FusedParams {
     int flen, fll;
     long long e0, e1;      // outputs of this call
     int in_step, out_step;
-    const double* gbank;   // whole stepping: per group of `ir` phases [smaxp][ir] shifted, zero-padded taps
+    const double* gbank;   // whole stepping: for EVERY first phase r0 in [0,out_step): [smaxp][ir] shifted, zero-padded taps
+                           // of phases r0..r0+ir-1 (phases past out_step-1 continue in the next stepping cycle)
     int gbank_len, smaxp;  // doubles in gbank; padded window length (multiple of 4)
-    int ir;                // phases per group (8 or 10)
-    const int* goff;       // [n_groups] floor(r0*in_step/out_step) of the group's first phase
+    int ir;                // phases per group (8)
+    int gbank_smem_len;    // doubles of the per-call bank selection kept in shared memory (n_groups * smaxp * ir)
+    int delta, wrap;       // first phase of group 0 (= e0 mod 8 when out_step % 8 == 0, else 0); wrap = rows may span cycles
+    const int* goff;       // [out_step] floor(r0*in_step/out_step)
     const int* phase_off;  // [out_step] floor(r*in_step/out_step)
     const int* phase_row;  // [out_step] (r*in_step) % out_step
     int fracs;
