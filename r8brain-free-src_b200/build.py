@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
         if os.path.exists(LIB):
             return LIB  # GPU box without a toolchain: use the prebuilt library
         raise RuntimeError("nvcc not found and no prebuilt libr8bgpu.so present")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = ["-DR8BGPU_PHASE_TIMERS"] if os.environ.get("R8BGPU_PHASE_TIMERS") else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

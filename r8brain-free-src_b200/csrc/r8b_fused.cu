@@ -48,11 +48,15 @@ constexpr int IQ = 3;               // ... x stepping cycles per lane
 
 __device__ __forceinline__ int ylay(int i, int ysh) { return i + (i >> ysh); }
 
-// W_M^idx (idx < M) from two 64-entry shared-memory tables: W^idx = W^(64a) * W^b, idx = 64a + b.
-// One extra complex multiply (<= ~1.5 ulp) instead of a 64 KB table walked through L1/L2.
-__device__ __forceinline__ double2 tw_split(const double2* __restrict__ twc, const double2* __restrict__ twf, int idx)
+// Twiddles from shared memory, laid out [q][r] so that the 16 consecutive lanes of a half-warp read 16
+// consecutive entries (the natural [r*q] indexing is an up-to-16-way bank conflict for even q):
+//   tw2t[q*16 + r] = W_256^(r q)            (r, q < 16)  -- passes with NCUR = 256
+//   tw1t[q*16 + r] = W_M^(r q)              (r, q < 16)
+//   W_M^(R q), R = 16 r_hi + r_lo < 256  =  tw2t[q*16 + r_hi] * tw1t[q*16 + r_lo]   -- passes with NCUR = M
+// (one extra complex multiply, <= ~1.5 ulp, instead of walking a 64 KB table through L1/L2).
+__device__ __forceinline__ double2 tw_pair(const double2* __restrict__ tw2t, const double2* __restrict__ tw1t, int r, int q)
 {
-    const double2 c = twc[idx >> 6], f = twf[idx & 63];
+    const double2 c = tw2t[q * 16 + (r >> 4)], f = tw1t[q * 16 + (r & 15)];
     return make_double2(fma(c.x, f.x, -c.y * f.y), fma(c.x, f.y, c.y * f.x));
 }
 
@@ -88,7 +92,7 @@ __device__ __forceinline__ void fwd_pass1_regs(double2 (&v)[16], double2* __rest
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         double2 x = v[bitrev<16>(q)];
-        if (q > 0) x = cmul<+1>(x, tw_split(twc, twf, r * q));
+        if (q > 0) x = cmul<+1>(x, tw_pair(twc, twf, r, q));
         s[fft_pad(r + q * 256)] = x;
     }
 }
@@ -107,7 +111,7 @@ __device__ __forceinline__ void fwd_pass(double2* __restrict__ s, const double2*
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         double2 x = v[bitrev<16>(q)];
-        if (D > 1 && q > 0) x = cmul<+1>(x, tw2_s[r * q]); // NCUR == 256: W_256^(r q) from shared memory
+        if (D > 1 && q > 0) x = cmul<+1>(x, tw2_s[q * 16 + r]); // NCUR == 256: W_256^(r q), [q][r] layout
         s[fft_pad(base + q * D)] = x;
     }
     (void) tw_g;
@@ -123,7 +127,7 @@ __device__ __forceinline__ void inv_pass(double2* __restrict__ s, const double2*
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         double2 x = s[fft_pad(base + q * D)];
-        if (D > 1 && q > 0) x = cmul<-1>(x, tw2_s[r * q]);
+        if (D > 1 && q > 0) x = cmul<-1>(x, tw2_s[q * 16 + r]);
         v[q] = x;
     }
     Network<16, -1>::run(v);
@@ -316,10 +320,10 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     extern __shared__ double2 smem[];
     double2* bufA = smem;              // forward spectrum Z, later Y_b / y_b
     double2* bufB = smem + FPL;        // Y_a / y_a
-    double2* tw2 = smem + 2 * FPL;     // W_256^k, k < 256
-    double2* twc = tw2 + 256;          // W_M^(64 a), a < 64
-    double2* twf = twc + 64;           // W_M^b, b < 64
-    double* sbank = reinterpret_cast<double*>(twf + 64); // whole-step bank (if it fits)
+    double2* tw2 = smem + 2 * FPL;     // tw2t[q*16+r] = W_256^(r q)
+    double2* twc = tw2;                // (same table: coarse factor of the NCUR = M twiddles)
+    double2* twf = tw2 + 256;          // tw1t[q*16+r] = W_M^(r q)
+    double* sbank = reinterpret_cast<double*>(twf + 256); // whole-step bank (if it fits)
     __shared__ int s_j[2];
     __shared__ int s_i[8];
     __shared__ double* s_o;
@@ -346,9 +350,11 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     double2 gv[16];
     if (tid < 256) gather_loads(gv, src, ch, wa, wb, has_b, tid);
     // tables into shared memory
-    for (int i = tid; i < 256; i += FNT) tw2[i] = __ldg(&p.tw[i * (FM / 256)]);
-    if (tid < 64) twc[tid] = __ldg(&p.tw[tid * 64]);
-    else if (tid < 128) twf[tid - 64] = __ldg(&p.tw[tid - 64]);
+    {
+        const int i = tid & 255, q = i >> 4, r = i & 15;
+        if (tid < 256) tw2[i] = __ldg(&p.tw[(r * q) * (FM / 256)]);
+        else twf[i] = __ldg(&p.tw[r * q]);
+    }
     if (MODE == 0) {
         const int n_groups = (p.out_step + IRV - 1) / IRV, esz = p.smaxp * IRV;
         if (BANKV) {
@@ -367,7 +373,10 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     }
     __syncthreads();
 
-    // optional phase timing (R8BGPU_PROFILE=1): thread 0 accumulates clock64() deltas per phase
+    // optional phase timing: build with R8BGPU_PHASE_TIMERS=1 (adds -DR8BGPU_PHASE_TIMERS) and run with
+    // R8BGPU_PROFILE=1; thread 0 accumulates clock64() deltas per phase.  Compiled out by default: the live
+    // 64-bit timestamp was being spilled around every barrier.
+#ifdef R8BGPU_PHASE_TIMERS
     long long t_prev = p.prof ? clock64() : 0;
 #define R8B_TICK(i)                                                                  \
     if (p.prof != nullptr && tid == 0) {                                             \
@@ -375,6 +384,9 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
         atomicAdd(&p.prof[i], (unsigned long long) (t_now - t_prev));                \
         t_prev = t_now;                                                              \
     }
+#else
+#define R8B_TICK(i)
+#endif
     if (tid < 256) fwd_pass1_regs(gv, bufA, twc, twf, tid);
     __syncthreads();
     R8B_TICK(0)
@@ -441,7 +453,7 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             double2 x = buf[fft_pad(g + q * 256)];
-            if (q > 0) x = cmul<-1>(x, tw_split(twc, twf, g * q));
+            if (q > 0) x = cmul<-1>(x, tw_pair(twc, twf, g, q));
             v[q] = x;
         }
         Network<16, -1>::run(v);
@@ -529,21 +541,23 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
             dst_write_f(dst, ch, p.e0 + k, acc);
         }
     }
+#ifdef R8BGPU_PHASE_TIMERS
     if (p.prof != nullptr) {
         __syncthreads();
         R8B_TICK(7)
     }
+#endif
 #undef R8B_TICK
 }
 
 int fused_smem_bytes(int bank_doubles_in_smem)
 {
-    return 2 * FPL * (int) sizeof(double2) + (256 + 128) * (int) sizeof(double2) + bank_doubles_in_smem * (int) sizeof(double);
+    return 2 * FPL * (int) sizeof(double2) + (256 + 256) * (int) sizeof(double2) + bank_doubles_in_smem * (int) sizeof(double);
 }
 
 int fused_max_span(int lg, int yl, int yr) { return 2 * (FM - 2 * lg) - yl - yr; }
 int fused_stage_doubles() { return (FNT / 32) * 256; }              // 32 rows x 8 doubles per warp
-int fused_fixed_doubles() { return 2 * (2 * FPL + 256 + 128); }     // buffers + twiddle tables
+int fused_fixed_doubles() { return 2 * (2 * FPL + 256 + 256); }     // buffers + twiddle tables
 
 template <int MODE, int IRV, bool PADV, bool BANKV>
 static void launch_inst(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, int smem, cudaStream_t st)
