@@ -167,6 +167,13 @@ struct StageDev {
     int* goff = nullptr;
     int gbank_len = 0, gbank_smem_len = 0, smaxp = 0, ir = 8;
     int yl = 0, yr = 0, ysh = 31, span_max = 0, bank_in_smem = 0;
+    // R8B_FASTTIMING position tables (FRAC_POLY stages of fast-timing plans)
+    int* ft_dp = nullptr;
+    double* ft_fpos = nullptr;
+    int* h_dp[2] = {nullptr, nullptr};
+    double* h_fpos[2] = {nullptr, nullptr};
+    cudaEvent_t ft_ev[2] = {nullptr, nullptr};
+    int ft_cur = 0;
     int casc_len = 0; // >= 2 on the first stage of a run of HBUP stages executed by k_hbup_cascade
 };
 
@@ -230,6 +237,13 @@ struct r8bgpu_batch {
             cudaFree(d.phase_row);
             cudaFree(d.gbank);
             cudaFree(d.goff);
+            cudaFree(d.ft_dp);
+            cudaFree(d.ft_fpos);
+            for (int k = 0; k < 2; k++) {
+                if (d.h_dp[k]) cudaFreeHost(d.h_dp[k]);
+                if (d.h_fpos[k]) cudaFreeHost(d.h_fpos[k]);
+                if (d.ft_ev[k]) cudaEventDestroy(d.ft_ev[k]);
+            }
         }
         cudaFree(st_in);
         cudaFree(st_out);
@@ -485,6 +499,16 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
             if (!cuda_ok(cudaMalloc(&d.bank, nb), "cudaMalloc(bank)")) return nullptr;
             if (!cuda_ok(cudaMemcpy(d.bank, s.bank.table.data(), nb, cudaMemcpyHostToDevice), "copy bank")) return nullptr;
             b->dev_bytes += nb;
+            if (s.kind == ST_FRAC_POLY && s.fasttiming) {
+                const size_t cap = (size_t) s.max_out_len + 16;
+                if (!cuda_ok(cudaMalloc(&d.ft_dp, cap * sizeof(int)), "cudaMalloc(ft)")) return nullptr;
+                if (!cuda_ok(cudaMalloc(&d.ft_fpos, cap * sizeof(double)), "cudaMalloc(ft)")) return nullptr;
+                for (int k = 0; k < 2; k++) {
+                    if (!cuda_ok(cudaMallocHost(&d.h_dp[k], cap * sizeof(int)), "cudaMallocHost(ft)")) return nullptr;
+                    if (!cuda_ok(cudaMallocHost(&d.h_fpos[k], cap * sizeof(double)), "cudaMallocHost(ft)")) return nullptr;
+                    cudaEventCreateWithFlags(&d.ft_ev[k], cudaEventDisableTiming);
+                }
+            }
             if (s.kind == ST_FRAC_WHOLE) {
                 // per output phase r: floor(r*InStep/OutStep) and the bank row (r*InStep) % OutStep
                 std::vector<int> off((size_t) s.out_step), row((size_t) s.out_step);
@@ -660,6 +684,29 @@ int r8bgpu_batch_sync(r8bgpu_batch* b)
     return cuda_ok(cudaStreamSynchronize(b->stream), "batch_sync") ? 0 : -1;
 }
 
+// R8B_FASTTIMING: ship this call's host-walked (position, fraction) sequence to the device, in stream order
+// ahead of the kernels that read it.  Two pinned staging buffers alternate; an event guards their reuse.
+static bool upload_fasttiming(r8bgpu_batch* b, cudaStream_t st)
+{
+    const Plan& P = *b->plan;
+    for (size_t i = 0; i < P.stages.size(); i++) {
+        const StageDesc& s = P.stages[i];
+        if (s.kind != ST_FRAC_POLY || !s.fasttiming) continue;
+        StageDev& d = b->dev[i];
+        const StageCall& c = b->calls[i];
+        const size_t n = c.ft_dp.size();
+        if (n == 0) continue;
+        const int k = (d.ft_cur ^= 1);
+        cudaEventSynchronize(d.ft_ev[k]);
+        memcpy(d.h_dp[k], c.ft_dp.data(), n * sizeof(int));
+        memcpy(d.h_fpos[k], c.ft_fpos.data(), n * sizeof(double));
+        if (!cuda_ok(cudaMemcpyAsync(d.ft_dp, d.h_dp[k], n * sizeof(int), cudaMemcpyHostToDevice, st), "fasttiming upload")) return false;
+        if (!cuda_ok(cudaMemcpyAsync(d.ft_fpos, d.h_fpos[k], n * sizeof(double), cudaMemcpyHostToDevice, st), "fasttiming upload")) return false;
+        cudaEventRecord(d.ft_ev[k], st);
+    }
+    return true;
+}
+
 // Launches every kernel of one process() call (already scheduled in b->calls) for the channel range
 // [ch0, ch0+nch) on stream st.  d_in / d_out point at the FIRST channel of that range.
 static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, int l, double* d_out,
@@ -805,6 +852,8 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.in_pos_shift = fc.in_pos_shift;
             p.fpos0 = fc.fpos0;
             p.p0 = fc.p0;
+            p.pos_dp = fd.ft_dp;
+            p.pos_fpos = fd.ft_fpos;
             if (b->prof == nullptr && getenv("R8BGPU_PROFILE")) {
                 cudaMalloc(&b->prof, 8 * sizeof(unsigned long long));
                 cudaMemset(b->prof, 0, 8 * sizeof(unsigned long long));
@@ -870,6 +919,8 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.in_pos_shift = c.in_pos_shift;
             p.fpos0 = c.fpos0;
             p.p0 = c.p0;
+            p.pos_dp = d.ft_dp;
+            p.pos_fpos = d.ft_fpos;
             if (s.kind == ST_FRAC_WHOLE) launch_frac_whole(p, src, dst, nch, st);
             else launch_frac_poly(p, src, dst, nch, st);
             b->launches++;
@@ -941,6 +992,7 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
         return -1;
     }
 
+    if (!upload_fasttiming(b, st)) return -1;
     launch_call(b, d_in, in_stride, l, d_out, out_stride, 0, b->n_ch, st);
     if (!cuda_ok(cudaGetLastError(), "batch_process: kernel launch")) return -1;
     return n_out;
@@ -999,6 +1051,7 @@ int r8bgpu_batch_process_host(r8bgpu_batch* b, const double* h_in, size_t in_str
     }
     // order after any device-path work queued on the batch stream (the two paths share the rings)
     if (!cuda_ok(cudaStreamSynchronize(b->stream), "process_host: sync(batch stream)")) return -1;
+    if (!P.passthrough && !upload_fasttiming(b, b->s_comp)) return -1;
     const int G = b->host_groups;
     for (int gi = 0; gi < G; gi++) {
         const int ch0 = (int) ((long long) b->n_ch * gi / G);

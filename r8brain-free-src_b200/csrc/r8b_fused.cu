@@ -500,7 +500,9 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
                 while (lo < hi) {
                     const long long mid = lo + (hi - lo) / 2;
                     long long pk = p.p0;
-                    if (mid > 0) {
+                    if (p.pos_dp != nullptr) {
+                        pk = mid < nk ? p.p0 + __ldg(p.pos_dp + mid) : 0x7fffffffffffffffLL;
+                    } else if (mid > 0) {
                         const int ic = p.in_counter0 + (int) mid;
                         const double np = __ddiv_rn(__dmul_rn(__dadd_rn((double) ic, p.in_pos_shift), p.ssr), p.dsr);
                         pk = p.p0 + (__double2int_rz(np) - p.in_pos_int0);
@@ -516,7 +518,10 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
         for (int k = ka + tid; k < kb; k += FNT) {
             long long ip = p.p0;
             double fpos = p.fpos0;
-            if (k > 0) {
+            if (p.pos_dp != nullptr) { // R8B_FASTTIMING: host-walked sequence
+                ip = p.p0 + __ldg(p.pos_dp + k);
+                fpos = __ldg(p.pos_fpos + k);
+            } else if (k > 0) {
                 const int ic = p.in_counter0 + k;
                 const double np = __ddiv_rn(__dmul_rn(__dadd_rn((double) ic, p.in_pos_shift), p.ssr), p.dsr);
                 const int ni = __double2int_rz(np);

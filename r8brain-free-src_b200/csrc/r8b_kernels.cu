@@ -239,7 +239,10 @@ __global__ void __launch_bounds__(256) k_frac_poly(FracParams p, SrcView src, Ds
     const int ch = blockIdx.y;
     long long ip = p.p0;
     double fpos = p.fpos0;
-    if (k > 0) {
+    if (p.pos_dp != nullptr) { // R8B_FASTTIMING: host-walked sequence
+        ip = p.p0 + __ldg(p.pos_dp + k);
+        fpos = __ldg(p.pos_fpos + k);
+    } else if (k > 0) {
         const int ic = p.in_counter0 + (int) k;
         const double np = __ddiv_rn(__dmul_rn(__dadd_rn((double) ic, p.in_pos_shift), p.ssr), p.dsr);
         const int ni = __double2int_rz(np);

@@ -54,6 +54,8 @@ struct FracParams {
     int in_counter0, in_pos_int0;
     double in_pos_shift, fpos0;
     long long p0;
+    const int* pos_dp;       // R8B_FASTTIMING: per-output position - p0 and fraction (else nullptr)
+    const double* pos_fpos;
 };
 
 struct HbParams {
@@ -112,6 +114,8 @@ struct FusedParams {
     int in_counter0, in_pos_int0;
     double in_pos_shift, fpos0;
     long long p0;
+    const int* pos_dp;       // R8B_FASTTIMING tables (else nullptr)
+    const double* pos_fpos;
 };
 int fused_smem_bytes(int bank_doubles_in_smem);
 int fused_max_span(int lg, int yl, int yr);

@@ -72,10 +72,7 @@ bool make_frac(StageDesc& s, double src, double dst, double atten, bool is_third
         s.out_step = b;
         design_frac_bank(b, atten, is_third, s.bank);
     } else {
-        if (fasttiming) {
-            err = "R8B_FASTTIMING non-whole-stepping interpolation is not implemented";
-            return false;
-        }
+        s.fasttiming = fasttiming != 0;
         s.kind = ST_FRAC_POLY;
         design_frac_bank(-1, atten, is_third, s.bank);
     }
@@ -473,6 +470,23 @@ int Schedule::advance(int l, std::vector<StageCall>& calls)
             const long long fl2 = s.bank.filter_len / 2;
             const long long pmax = c.n1 - 1 - fl2; // produce while p <= pmax
             long long cnt = 0;
+            if (s.fasttiming) {
+                // CDSPFracInterpolator.h:1153-1158: fpos += FracStep; PosIncr = (int) fpos; fpos -= PosIncr
+                const double frac_step = s.src_rate / s.dst_rate; // :713
+                c.p_last = ps.p;
+                while (ps.p <= pmax) {
+                    c.ft_dp.push_back((int) (ps.p - c.p0));
+                    c.ft_fpos.push_back(ps.fpos);
+                    c.p_last = ps.p;
+                    cnt++;
+                    ps.fpos += frac_step;
+                    const int inc = (int) ps.fpos;
+                    ps.fpos -= inc;
+                    ps.p += inc;
+                }
+                e1 = c.e0 + cnt;
+                break;
+            }
             if (ps.p <= pmax) {
                 // largest k with p_k <= pmax (p_k is non-decreasing in k); k = 0 qualifies.
                 long long lo = 0;

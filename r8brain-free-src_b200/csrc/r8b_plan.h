@@ -48,6 +48,7 @@ struct StageDesc {
     double src_rate = 0, dst_rate = 0; // as seen by this stage
     bool is_third = false;
     int in_step = 0, out_step = 0;
+    bool fasttiming = false; // R8B_FASTTIMING: drifting accumulator instead of the resettable counter
     FracBank bank;
     // --- Halfband
     int hb_taps = 0;
@@ -94,6 +95,10 @@ struct StageCall {
     double in_pos_shift = 0.0, fpos0 = 0.0;
     long long p0 = 0;
     long long p_last = 0; // read position of the last output of this call (FracPoly)
+    // R8B_FASTTIMING: the position sequence is inherently sequential (fpos += step with rounding), so the
+    // host walks it and hands the kernel one (position - p0, fraction) pair per output of the call
+    std::vector<int> ft_dp;
+    std::vector<double> ft_fpos;
 };
 
 struct Schedule {

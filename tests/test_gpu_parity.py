@@ -239,3 +239,26 @@ def test_long_filters(pkg, ref):
     for src, dst, tb in [(96000.0, 48000.0, 1.0), (44100.0, 48000.0, 1.0), (48000.0, 44100.0, 3.0)]:
         ys, yr = run_both(pkg, ref, src, dst, [8192] * 4, n_ch=1, tb=tb, max_in=8192)
         check(ys, yr)
+
+
+def test_fasttiming_parity(pkg):
+    """R8B_FASTTIMING=1 plans against the reference compiled with the same macro."""
+    if not ou.have_ref("e0_ft"):
+        pytest.skip("oracle/_ref fast-timing build missing")
+    ref_ft = ou.RefOracle("e0_ft")
+    for src, dst in [(48000.0, 47999.0), (44100.0, 22050.5), (192000.0, 44101.0)]:
+        lens = [4096] * 10 + [1000, 1, 0, 17, 4096]
+        x = ou.white_noise(2, sum(lens), 5)
+        plan = pkg.Plan(src, dst, 4096, 2.0, pkg.ATTEN_24, fasttiming=1)
+        b = pkg.Batch(plan, 2, 0)
+        rs = [ref_ft.Resampler(src, dst, 4096, 2.0, pkg.ATTEN_24) for _ in range(2)]
+        pos, ya, yb = 0, [[], []], [[], []]
+        for l in lens:
+            y = b.process_host(x[:, pos:pos + l])
+            for c in range(2):
+                r = rs[c].process(x[c, pos:pos + l])
+                assert len(r) == y.shape[1]
+                ya[c].append(y[c])
+                yb[c].append(r)
+            pos += l
+        check([np.concatenate(a) for a in ya], [np.concatenate(a) for a in yb])

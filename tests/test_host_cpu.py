@@ -160,3 +160,17 @@ def test_product_never_touches_oracle():
                 assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle" not in txt.lower(), f
     inc = open(os.path.join(ROOT, "include", "r8bgpu.h")).read()
     assert "oracle" not in inc.lower()
+
+
+def test_fasttiming_scheduler_matches_reference(pkg):
+    """R8B_FASTTIMING=1 (r8bconf.h:123-132): the drifting-accumulator timing of the non-whole interpolator."""
+    if not ou.have_ref("e0_ft"):
+        pytest.skip("oracle/_ref fast-timing build missing")
+    ref_ft = ou.RefOracle("e0_ft")
+    assert ref_ft.L.r8bref_fasttiming() == 1
+    for src, dst in [(48000.0, 47999.0), (44100.0, 22050.5), (44100.0, 96001.0), (44100.0, 96000.0)]:
+        lens = [4096] * 6 + [1000, 0, 1, 4096]
+        plan = pkg.Plan(src, dst, 4096, 2.0, pkg.ATTEN_24, fasttiming=1)
+        r = ref_ft.Resampler(src, dst, 4096, 2.0, pkg.ATTEN_24)
+        x = np.zeros(4096)
+        assert plan.simulate(lens) == [len(r.process(x[:l])) for l in lens]
