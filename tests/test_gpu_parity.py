@@ -262,3 +262,29 @@ def test_fasttiming_parity(pkg):
                 yb[c].append(r)
             pos += l
         check([np.concatenate(a) for a in ya], [np.concatenate(a) for a in yb])
+
+
+def test_tiny_blocks_and_many_channels(pkg, ref):
+    # MaxInLen of a few samples (thousands of calls before the first output) and a wide batch
+    for max_in, n_calls in [(1, 2600), (7, 500)]:
+        x = ou.white_noise(1, max_in * n_calls, 9)
+        rb = pkg.ResamplerBatch(1, 44100.0, 96000.0, max_in, device=0)
+        r = ref.Resampler(44100.0, 96000.0, max_in, 2.0, pkg.ATTEN_24)
+        ya, yb = [], []
+        for c in range(n_calls):
+            a = rb.process(x[:, c * max_in:(c + 1) * max_in])
+            b = r.process(x[0, c * max_in:(c + 1) * max_in])
+            assert a.shape[1] == len(b)
+            ya.append(a[0])
+            yb.append(b)
+        check([np.concatenate(ya)], [np.concatenate(yb)])
+    n_ch = 3000
+    x = ou.white_noise(n_ch, 3 * 1024, 13)
+    rb = pkg.ResamplerBatch(n_ch, 48000.0, 44100.0, 1024, device=0)
+    y = np.concatenate([rb.process(x[:, i:i + 1024]) for i in range(0, 3072, 1024)], axis=1)
+    for c in (0, 1, 1499, 2999):
+        r = ref.Resampler(48000.0, 44100.0, 1024, 2.0, pkg.ATTEN_24)
+        yr = np.concatenate([r.process(x[c, i:i + 1024]) for i in range(0, 3072, 1024)])
+        assert len(yr) == y.shape[1]
+        m, rr = ou.parity_metrics(y[c], yr)
+        assert m <= MAX_TOL and rr <= RMS_TOL
