@@ -22,6 +22,7 @@
 
 #include <cstddef>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -194,35 +195,29 @@ public:
         return n < 0 ? 0 : n;
     }
 
-    /// As CDSPResampler.h:592-651.
+    /// One-shot conversion of a whole signal (semantics of CDSPResampler.h:592-651): the input is fed in
+    /// MaxInLen-sized pieces, followed by silence, until `oplen` output samples have been collected; the
+    /// stream state is cleared afterwards.  Tin/Tout may be any arithmetic sample type.
     template <typename Tin, typename Tout>
     void oneshot(const Tin* ip, int iplen, Tout* op, int oplen)
     {
-        std::vector<double> Buf((size_t) MaxInLen);
-        bool IsZero = false;
-        while (oplen > 0) {
-            int rc;
-            double* p;
-            if (iplen == 0) {
-                rc = MaxInLen;
-                p = &Buf[0];
-                if (!IsZero) {
-                    IsZero = true;
-                    memset(p, 0, (size_t) MaxInLen * sizeof(double));
-                }
-            } else {
-                rc = iplen < MaxInLen ? iplen : MaxInLen;
-                p = &Buf[0];
-                for (int i = 0; i < rc; i++) p[i] = (double) ip[i];
-                ip += rc;
-                iplen -= rc;
+        std::vector<double> chunk((size_t) MaxInLen, 0.0);
+        int fed = 0, got = 0;
+        while (got < oplen) {
+            const int n = (fed < iplen) ? ((iplen - fed < MaxInLen) ? iplen - fed : MaxInLen) : MaxInLen;
+            if (fed < iplen) {
+                for (int i = 0; i < n; i++) chunk[(size_t) i] = (double) ip[fed + i];
+                fed += n;
+                if (fed >= iplen && n < MaxInLen) std::fill(chunk.begin() + n, chunk.end(), 0.0);
+            } else if (fed == iplen) {
+                std::fill(chunk.begin(), chunk.end(), 0.0); // from here on: silence
+                fed++;
             }
-            double* op0;
-            int wc = process(p, rc, op0);
-            if (wc > oplen) wc = oplen;
-            for (int i = 0; i < wc; i++) op[i] = (Tout) op0[i];
-            op += wc;
-            oplen -= wc;
+            double* res = NULL;
+            int produced = process(&chunk[0], n, res);
+            if (produced > oplen - got) produced = oplen - got;
+            for (int i = 0; i < produced; i++) op[got + i] = (Tout) res[i];
+            got += produced;
         }
         clear();
     }
