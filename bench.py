@@ -329,6 +329,22 @@ def main():
                "h2d_bytes_per_step": n_ch * BLOCK * 8, "d2h_bytes_per_step": int(n_ch * (outs / ke) * 8),
                "steps": ke, "api": "r8bgpu_batch_process_host (pinned host in/out, sync per call)"}
 
+        if world == 1:
+            # same call with float32 planar host buffers (r8bgpu_batch_process_host_fmt): what a caller holding
+            # 32-bit audio pays -- half the PCIe bytes, widening/narrowing on the device (r8b_format.cu)
+            fx = [torch.from_numpy(synth_block(n_ch, BLOCK, 3000 + i).astype("float32")).pin_memory() for i in range(2)]
+            fy = torch.empty((n_ch, cap), dtype=torch.float32).pin_memory()
+            bo = pkg.Buffer.make(fy.data_ptr(), pkg.F32, False, cap)
+            bis = [pkg.Buffer.make(t.data_ptr(), pkg.F32, False, BLOCK) for t in fx]
+            for i in range(2):
+                batch.process_fmt(bis[i & 1], BLOCK, bo, cap, host=True)
+            t0 = time.perf_counter()
+            for i in range(ke):
+                batch.process_fmt(bis[i & 1], BLOCK, bo, cap, host=True)
+            torch.cuda.synchronize(dev)
+            e2e["float32_io"] = {"value": 1e-6 * n_ch * BLOCK * ke / (time.perf_counter() - t0), "unit": "Msamples/s",
+                                 "api": "r8bgpu_batch_process_host_fmt (R8BGPU_F32 planar in/out)"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_run(src, dst, tb, atten, extfft, threads, target_seconds=8.0)

@@ -105,6 +105,20 @@ public:
         return r8bgpu_batch_process(Batch, d_ip, InStride, l, d_op, OutStride, OutCap);
     }
 
+    /// Typed buffers (int16 / packed int24 / int32 / float32 / float64, planar or interleaved): the
+    /// sample conversions of oneshot<Tin,Tout>() (CDSPResampler.h:592-651) run on the device.
+    int process(const r8bgpu_buffer& ip, const int l, const r8bgpu_buffer& op, const int OutCap)
+    {
+        if (!ensure()) return -1;
+        return r8bgpu_batch_process_host_fmt(Batch, &ip, l, &op, OutCap);
+    }
+
+    int processDevice(const r8bgpu_buffer& d_ip, const int l, const r8bgpu_buffer& d_op, const int OutCap)
+    {
+        if (!ensure()) return -1;
+        return r8bgpu_batch_process_fmt(Batch, &d_ip, l, &d_op, OutCap);
+    }
+
     void setStream(void* CudaStream)
     {
         if (ensure()) r8bgpu_batch_set_stream(Batch, CudaStream);

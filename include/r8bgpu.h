@@ -20,6 +20,8 @@
  *                                                                                example.cpp:61-67,
  *                                                                                CDSPResampler.h:559-575
  *                                 (and r8b_process()                             DLL/r8bsrc.cpp:101-105)
+ *   r8bgpu_batch_process_fmt / _host_fmt   same, plus the sample conversion loops of
+ *                                 oneshot<Tin,Tout>()                            CDSPResampler.h:592-651
  *   r8bgpu_batch_process_host     same, with host buffers (H2D + kernels + D2H); this is what the
  *                                 single-object r8b::CDSPResampler::process() shim in
  *                                 include/r8b/CDSPResampler.h calls.
@@ -125,6 +127,39 @@ R8BGPU_API int r8bgpu_batch_process(r8bgpu_batch* batch, const double* d_in, siz
 R8BGPU_API int r8bgpu_batch_process_host(r8bgpu_batch* batch, const double* h_in, size_t in_ch_stride,
                                          int l, double* h_out, size_t out_ch_stride, int out_cap);
 R8BGPU_API int r8bgpu_batch_sync(r8bgpu_batch* batch);
+
+/* ---- caller-side sample formats ---------------------------------------------------------
+ * What the reference's callers do on the CPU around process(): CDSPResampler::oneshot<Tin,Tout>()
+ * converts "(double) ip[i]" on the way in and "(Tout) op[i]" on the way out (CDSPResampler.h:592-651),
+ * and WAV front-ends de-interleave frames (bench/r8bfreesrc.cpp:106-137).  Here the narrow samples
+ * cross PCIe / HBM as they are and are widened / narrowed on the device.
+ *   in : x = (double) v * scale        out: v = (T) (y * scale)
+ * With scale = 1 these are exactly the C++ conversions of oneshot(): widening is exact, float output
+ * rounds to nearest, integer output truncates toward zero (out-of-range values, undefined in the
+ * reference, saturate; NaN -> 0).  R8BGPU_S24 is packed 3-byte little-endian. */
+typedef enum {
+    R8BGPU_F64 = 0,
+    R8BGPU_F32 = 1,
+    R8BGPU_S16 = 2,
+    R8BGPU_S24 = 3,
+    R8BGPU_S32 = 4
+} r8bgpu_sample_format;
+
+typedef struct {
+    void* data;      /* host (…_host_fmt) or device (…_fmt) memory; never written when used as input */
+    int format;      /* r8bgpu_sample_format */
+    int interleaved; /* 0: planar, channel c starts at c*stride; 1: frame f starts at f*stride, channel c at +c */
+    size_t stride;   /* in samples of `format` */
+    double scale;    /* see above; 1.0 for the reference's plain casts */
+} r8bgpu_buffer;
+
+/* As r8bgpu_batch_process() / r8bgpu_batch_process_host() with typed buffers.  out_cap = room per
+ * channel in samples. */
+R8BGPU_API int r8bgpu_batch_process_fmt(r8bgpu_batch* batch, const r8bgpu_buffer* d_in, int l,
+                                        const r8bgpu_buffer* d_out, int out_cap);
+R8BGPU_API int r8bgpu_batch_process_host_fmt(r8bgpu_batch* batch, const r8bgpu_buffer* h_in, int l,
+                                             const r8bgpu_buffer* h_out, int out_cap);
+
 /* Number of kernels this batch has launched since creation. */
 R8BGPU_API unsigned long long r8bgpu_batch_kernel_launches(const r8bgpu_batch* batch);
 /* Per-stage device timing for profiling/bench: when enabled every stage launch is bracketed

@@ -62,6 +62,8 @@ _SYMBOLS = {
     "r8bgpu_batch_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "r8bgpu_batch_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int]),
     "r8bgpu_batch_process_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int]),
+    "r8bgpu_batch_process_fmt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "r8bgpu_batch_process_host_fmt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "r8bgpu_batch_sync": (C.c_int, [C.c_void_p]),
     "r8bgpu_batch_kernel_launches": (C.c_ulonglong, [C.c_void_p]),
     "r8bgpu_batch_device_bytes": (C.c_ulonglong, [C.c_void_p]),
@@ -75,6 +77,21 @@ _SYMBOLS = {
 
 class R8bGpuError(RuntimeError):
     pass
+
+
+# r8bgpu_sample_format / r8bgpu_buffer (include/r8bgpu.h)
+F64, F32, S16, S24, S32 = 0, 1, 2, 3, 4
+FORMAT_BYTES = {F64: 8, F32: 4, S16: 2, S24: 3, S32: 4}
+_NP_FORMATS = {"float64": F64, "float32": F32, "int16": S16, "int32": S32}
+
+
+class Buffer(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("format", C.c_int), ("interleaved", C.c_int),
+                ("stride", C.c_size_t), ("scale", C.c_double)]
+
+    @classmethod
+    def make(cls, ptr, fmt, interleaved, stride, scale=1.0):
+        return cls(C.c_void_p(int(ptr) if ptr else None), int(fmt), int(bool(interleaved)), int(stride), float(scale))
 
 
 def lib_path():
@@ -251,6 +268,36 @@ class Batch:
         if n < 0:
             raise R8bGpuError(_err())
         return n
+
+    def process_fmt(self, buf_in, l, buf_out, out_cap, host):
+        """Typed buffers (Buffer.make(...)): host=True -> r8bgpu_batch_process_host_fmt, else device."""
+        fn = lib().r8bgpu_batch_process_host_fmt if host else lib().r8bgpu_batch_process_fmt
+        n = fn(self._h, C.byref(buf_in), int(l), C.byref(buf_out), int(out_cap))
+        if n < 0:
+            raise R8bGpuError(_err())
+        return n
+
+    def process_host_fmt(self, x, out_dtype=None, interleaved=False, in_scale=1.0, out_scale=1.0, fmt=None,
+                         out_fmt=None):
+        """x: numpy array of int16/int32/float32/float64 samples, planar [n_channels, l] or (interleaved=True)
+        [l, n_channels]; packed 24-bit is uint8 [..., 3] with fmt=S24.  Returns the same layout in out_dtype
+        (default: the input's) -- the conversions of oneshot<Tin,Tout>() (CDSPResampler.h:592-651)."""
+        x = np.ascontiguousarray(x)
+        fi = _NP_FORMATS[x.dtype.name] if fmt is None else fmt
+        shape = x.shape[:2]
+        l, nch = (shape[0], shape[1]) if interleaved else (shape[1], shape[0])
+        if nch != self.n_channels:
+            raise ValueError("channel count mismatch")
+        if out_fmt is None:
+            out_fmt = fi if out_dtype is None else _NP_FORMATS[np.dtype(out_dtype).name]
+        cap = max(self.plan.max_out_len, 1)
+        np_out = {F64: np.float64, F32: np.float32, S16: np.int16, S32: np.int32, S24: np.uint8}[out_fmt]
+        tail = (3,) if out_fmt == S24 else ()
+        y = np.empty(((cap, nch) if interleaved else (nch, cap)) + tail, dtype=np_out)
+        bi = Buffer.make(x.ctypes.data, fi, interleaved, nch if interleaved else l, in_scale)
+        bo = Buffer.make(y.ctypes.data, out_fmt, interleaved, nch if interleaved else cap, out_scale)
+        n = self.process_fmt(bi, l, bo, cap, host=True)
+        return (y[:n] if interleaved else y[:, :n]).copy()
 
     def process_host(self, x):
         """x: float64 numpy [n_channels, l] (C-contiguous rows).  Returns [n_channels, n_out]."""

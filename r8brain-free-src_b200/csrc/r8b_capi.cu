@@ -206,6 +206,8 @@ struct r8bgpu_batch {
     // staging + pipeline resources for the host-pointer entry point
     double* st_in = nullptr;
     double* st_out = nullptr;
+    unsigned char* raw_in = nullptr;   // narrow-format staging (r8b_format.cu)
+    unsigned char* raw_out = nullptr;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp = nullptr;
     int host_groups = 1;
     std::vector<cudaEvent_t> ev_h2d, ev_k;
@@ -247,6 +249,8 @@ struct r8bgpu_batch {
         }
         cudaFree(st_in);
         cudaFree(st_out);
+        cudaFree(raw_in);
+        cudaFree(raw_out);
         for (auto e : ev_h2d) cudaEventDestroy(e);
         for (auto e : ev_k) cudaEventDestroy(e);
         if (s_h2d) cudaStreamDestroy(s_h2d);
@@ -643,8 +647,8 @@ int r8bgpu_batch_stage_kernel(const r8bgpu_batch* b, int stage, char* name, int 
     } else {
         switch (s.kind) {
         case ST_BLOCKCONV: nm = "k_blockconv"; break;
-        case ST_FRAC_WHOLE: nm = "k_frac_whole"; break;
-        case ST_FRAC_POLY: nm = "k_frac_poly"; break;
+        case ST_FRAC_WHOLE: nm = "k_frac<false>"; break;
+        case ST_FRAC_POLY: nm = "k_frac<true>"; break;
         case ST_HBUP: nm = "k_hbup"; break;
         default: nm = "k_hbdown"; break;
         }
@@ -998,49 +1002,93 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
     return n_out;
 }
 
+// ---- staging shared by the host path and the sample-format paths ----------------------------
+} // extern "C" (helpers below have C++ linkage)
+
+static bool ensure_staging(r8bgpu_batch* b)
+{
+    if (b->st_in != nullptr) return true;
+    const Plan& P = *b->plan;
+    const size_t in_cap = (size_t) P.max_in_len;
+    const size_t o_cap = ((size_t) P.max_out_len + 3) & ~(size_t) 3; // rows 32-byte aligned
+    if (!cuda_ok(cudaMalloc(&b->st_in, in_cap * b->n_ch * sizeof(double)), "staging: cudaMalloc(in)")) return false;
+    if (!cuda_ok(cudaMalloc(&b->st_out, o_cap * b->n_ch * sizeof(double)), "staging: cudaMalloc(out)")) return false;
+    b->dev_bytes += (in_cap + o_cap) * b->n_ch * sizeof(double);
+    if (!cuda_ok(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking), "staging: stream")) return false;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking), "staging: stream")) return false;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&b->s_comp, cudaStreamNonBlocking), "staging: stream")) return false;
+    int groups = 8;
+    if (const char* e = getenv("R8BGPU_HOST_GROUPS")) groups = atoi(e);
+    if (groups < 1) groups = 1;
+    while (groups > 1 && b->n_ch / groups < 32) groups /= 2; // keep every group a full-GPU launch
+    b->host_groups = groups;
+    b->ev_h2d.resize((size_t) groups);
+    b->ev_k.resize((size_t) groups);
+    for (int i = 0; i < groups; i++) {
+        cudaEventCreateWithFlags(&b->ev_h2d[(size_t) i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&b->ev_k[(size_t) i], cudaEventDisableTiming);
+    }
+    return true;
+}
+
+static bool buffer_is_plain(const r8bgpu_buffer& d)
+{
+    return d.format == R8BGPU_F64 && !d.interleaved && d.scale == 1.0;
+}
+
+static bool check_buffer(const r8bgpu_batch* b, const r8bgpu_buffer* d, const char* what)
+{
+    if (d == nullptr || format_bytes(d->format) == 0) {
+        set_err(std::string(what) + ": unknown sample format");
+        return false;
+    }
+    if (d->interleaved && d->stride < (size_t) b->n_ch) {
+        set_err(std::string(what) + ": interleaved stride smaller than the channel count");
+        return false;
+    }
+    if (!(d->scale == d->scale) || d->scale == 0.0) {
+        set_err(std::string(what) + ": scale must be a non-zero number");
+        return false;
+    }
+    return true;
+}
+
 // Host-pointer path.  The batch is cut into channel groups that flow through a three-stage pipeline
 //   copy stream A: H2D(group g+1)  |  compute stream: kernels(group g)  |  copy stream B: D2H(group g-1)
 // so the two PCIe directions and the SMs work at the same time (channels are independent, so a group
 // is a self-contained sub-batch).  Staging buffers are per channel, so groups never alias.
-int r8bgpu_batch_process_host(r8bgpu_batch* b, const double* h_in, size_t in_stride, int l, double* h_out,
-                              size_t out_stride, int out_cap)
+// Narrow / interleaved sample formats cross PCIe as they are and are widened (narrowed) on the
+// device by r8b_format.cu, in the compute stage of the same pipeline.
+static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, const r8bgpu_buffer& out, int out_cap)
 {
-    if (b == nullptr || l < 0 || l > b->plan->max_in_len) {
+    if (l < 0 || l > b->plan->max_in_len) {
         set_err("batch_process_host: l must be in [0, MaxInLen]");
         return -1;
     }
-    if (l > 0 && h_in == nullptr) {
+    if (l > 0 && in.data == nullptr) {
         set_err("batch_process_host: null input");
         return -1;
     }
     DeviceGuard g(b->device);
     const Plan& P = *b->plan;
     const size_t in_cap = (size_t) P.max_in_len;
-    const size_t o_cap = ((size_t) P.max_out_len + 3) & ~(size_t) 3; // rows 32-byte aligned
-    if (b->st_in == nullptr) {
-        if (!cuda_ok(cudaMalloc(&b->st_in, in_cap * b->n_ch * sizeof(double)), "process_host: cudaMalloc(in)")) return -1;
-        if (!cuda_ok(cudaMalloc(&b->st_out, o_cap * b->n_ch * sizeof(double)), "process_host: cudaMalloc(out)")) return -1;
-        b->dev_bytes += (in_cap + o_cap) * b->n_ch * sizeof(double);
-        if (!cuda_ok(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking), "process_host: stream")) return -1;
-        if (!cuda_ok(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking), "process_host: stream")) return -1;
-        if (!cuda_ok(cudaStreamCreateWithFlags(&b->s_comp, cudaStreamNonBlocking), "process_host: stream")) return -1;
-        int groups = 8;
-        if (const char* e = getenv("R8BGPU_HOST_GROUPS")) groups = atoi(e);
-        if (groups < 1) groups = 1;
-        while (groups > 1 && b->n_ch / groups < 32) groups /= 2; // keep every group a full-GPU launch
-        b->host_groups = groups;
-        b->ev_h2d.resize((size_t) groups);
-        b->ev_k.resize((size_t) groups);
-        for (int i = 0; i < groups; i++) {
-            cudaEventCreateWithFlags(&b->ev_h2d[(size_t) i], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&b->ev_k[(size_t) i], cudaEventDisableTiming);
-        }
+    const size_t o_cap = ((size_t) P.max_out_len + 3) & ~(size_t) 3;
+    if (!ensure_staging(b)) return -1;
+    const bool in_plain = buffer_is_plain(in), out_plain = buffer_is_plain(out);
+    const size_t ein = (size_t) format_bytes(in.format), eout = (size_t) format_bytes(out.format);
+    if (!in_plain && b->raw_in == nullptr) {
+        if (!cuda_ok(cudaMalloc(&b->raw_in, in_cap * b->n_ch * 8), "process_host: cudaMalloc(raw in)")) return -1;
+        b->dev_bytes += in_cap * b->n_ch * 8;
+    }
+    if (!out_plain && b->raw_out == nullptr) {
+        if (!cuda_ok(cudaMalloc(&b->raw_out, o_cap * b->n_ch * 8), "process_host: cudaMalloc(raw out)")) return -1;
+        b->dev_bytes += o_cap * b->n_ch * 8;
     }
     int n = l;
     if (!P.passthrough) {
         Schedule saved = b->sched;
         n = b->sched.advance(l, b->calls);
-        if (n > out_cap || (n > 0 && h_out == nullptr)) {
+        if (n > out_cap || (n > 0 && out.data == nullptr)) {
             b->sched = saved;
             set_err("process_host: output capacity too small for this call");
             return -1;
@@ -1053,6 +1101,8 @@ int r8bgpu_batch_process_host(r8bgpu_batch* b, const double* h_in, size_t in_str
     if (!cuda_ok(cudaStreamSynchronize(b->stream), "process_host: sync(batch stream)")) return -1;
     if (!P.passthrough && !upload_fasttiming(b, b->s_comp)) return -1;
     const int G = b->host_groups;
+    const unsigned char* hin = (const unsigned char*) in.data;
+    unsigned char* hout = (unsigned char*) out.data;
     for (int gi = 0; gi < G; gi++) {
         const int ch0 = (int) ((long long) b->n_ch * gi / G);
         const int ch1 = (int) ((long long) b->n_ch * (gi + 1) / G);
@@ -1060,30 +1110,152 @@ int r8bgpu_batch_process_host(r8bgpu_batch* b, const double* h_in, size_t in_str
         if (nch <= 0) continue;
         double* din = b->st_in + (size_t) ch0 * in_cap;
         double* dout = b->st_out + (size_t) ch0 * o_cap;
-        if (l > 0 && !cuda_ok(cudaMemcpy2DAsync(din, in_cap * sizeof(double), h_in + (size_t) ch0 * in_stride,
-                                                in_stride * sizeof(double), (size_t) l * sizeof(double),
-                                                (size_t) nch, cudaMemcpyHostToDevice, b->s_h2d),
-                              "process_host: H2D"))
-            return -1;
+        unsigned char* rin = in_plain ? nullptr : b->raw_in + (size_t) ch0 * in_cap * 8;
+        unsigned char* rout = out_plain ? nullptr : b->raw_out + (size_t) ch0 * o_cap * 8;
+        if (l > 0) {
+            cudaError_t e;
+            if (in_plain)
+                e = cudaMemcpy2DAsync(din, in_cap * 8, hin + (size_t) ch0 * in.stride * 8, in.stride * 8,
+                                      (size_t) l * 8, (size_t) nch, cudaMemcpyHostToDevice, b->s_h2d);
+            else if (in.interleaved) // device copy: compact [l][nch]
+                e = cudaMemcpy2DAsync(rin, (size_t) nch * ein, hin + (size_t) ch0 * ein, in.stride * ein,
+                                      (size_t) nch * ein, (size_t) l, cudaMemcpyHostToDevice, b->s_h2d);
+            else // device copy: [nch][in_cap]
+                e = cudaMemcpy2DAsync(rin, in_cap * ein, hin + (size_t) ch0 * in.stride * ein, in.stride * ein,
+                                      (size_t) l * ein, (size_t) nch, cudaMemcpyHostToDevice, b->s_h2d);
+            if (!cuda_ok(e, "process_host: H2D")) return -1;
+        }
         cudaEventRecord(b->ev_h2d[(size_t) gi], b->s_h2d);
         cudaStreamWaitEvent(b->s_comp, b->ev_h2d[(size_t) gi], 0);
+        if (!in_plain) {
+            launch_to_f64(in.format, rin, in.interleaved != 0, in.interleaved ? (size_t) nch : in_cap, din, in_cap, l,
+                          nch, in.scale, b->s_comp);
+            b->launches++;
+        }
         if (P.passthrough) {
             if (l > 0) cudaMemcpy2DAsync(dout, o_cap * sizeof(double), din, in_cap * sizeof(double),
                                          (size_t) l * sizeof(double), (size_t) nch, cudaMemcpyDeviceToDevice, b->s_comp);
         } else {
             launch_call(b, din, in_cap, l, dout, o_cap, ch0, nch, b->s_comp);
         }
+        if (!out_plain) {
+            launch_from_f64(out.format, rout, out.interleaved != 0, out.interleaved ? (size_t) nch : o_cap, dout, o_cap,
+                            n, nch, out.scale, b->s_comp);
+            b->launches++;
+        }
         cudaEventRecord(b->ev_k[(size_t) gi], b->s_comp);
         cudaStreamWaitEvent(b->s_d2h, b->ev_k[(size_t) gi], 0);
-        if (n > 0 && !cuda_ok(cudaMemcpy2DAsync(h_out + (size_t) ch0 * out_stride, out_stride * sizeof(double), dout,
-                                                o_cap * sizeof(double), (size_t) n * sizeof(double), (size_t) nch,
-                                                cudaMemcpyDeviceToHost, b->s_d2h),
-                              "process_host: D2H"))
-            return -1;
+        if (n > 0) {
+            cudaError_t e;
+            if (out_plain)
+                e = cudaMemcpy2DAsync(hout + (size_t) ch0 * out.stride * 8, out.stride * 8, dout, o_cap * 8,
+                                      (size_t) n * 8, (size_t) nch, cudaMemcpyDeviceToHost, b->s_d2h);
+            else if (out.interleaved)
+                e = cudaMemcpy2DAsync(hout + (size_t) ch0 * eout, out.stride * eout, rout, (size_t) nch * eout,
+                                      (size_t) nch * eout, (size_t) n, cudaMemcpyDeviceToHost, b->s_d2h);
+            else
+                e = cudaMemcpy2DAsync(hout + (size_t) ch0 * out.stride * eout, out.stride * eout, rout, o_cap * eout,
+                                      (size_t) n * eout, (size_t) nch, cudaMemcpyDeviceToHost, b->s_d2h);
+            if (!cuda_ok(e, "process_host: D2H")) return -1;
+        }
     }
     if (!cuda_ok(cudaStreamSynchronize(b->s_d2h), "process_host: sync")) return -1;
     if (!cuda_ok(cudaStreamSynchronize(b->s_comp), "process_host: sync")) return -1;
     if (!cuda_ok(cudaGetLastError(), "process_host: kernel launch")) return -1;
+    return n;
+}
+
+extern "C" {
+
+int r8bgpu_batch_process_host(r8bgpu_batch* b, const double* h_in, size_t in_stride, int l, double* h_out,
+                              size_t out_stride, int out_cap)
+{
+    if (b == nullptr) {
+        set_err("batch_process_host: null batch");
+        return -1;
+    }
+    const r8bgpu_buffer in = { const_cast<double*>(h_in), R8BGPU_F64, 0, in_stride, 1.0 };
+    const r8bgpu_buffer out = { h_out, R8BGPU_F64, 0, out_stride, 1.0 };
+    return process_host_impl(b, in, l, out, out_cap);
+}
+
+int r8bgpu_batch_process_host_fmt(r8bgpu_batch* b, const r8bgpu_buffer* h_in, int l, const r8bgpu_buffer* h_out,
+                                  int out_cap)
+{
+    if (b == nullptr) {
+        set_err("batch_process_host_fmt: null batch");
+        return -1;
+    }
+    if (!check_buffer(b, h_in, "batch_process_host_fmt(in)") || !check_buffer(b, h_out, "batch_process_host_fmt(out)"))
+        return -1;
+    return process_host_impl(b, *h_in, l, *h_out, out_cap);
+}
+
+// Device buffers in any format: widen into the staging block, run, narrow into the caller's buffer --
+// all on the batch stream, asynchronous like r8bgpu_batch_process().
+int r8bgpu_batch_process_fmt(r8bgpu_batch* b, const r8bgpu_buffer* d_in, int l, const r8bgpu_buffer* d_out,
+                             int out_cap)
+{
+    if (b == nullptr) {
+        set_err("batch_process_fmt: null batch");
+        return -1;
+    }
+    if (!check_buffer(b, d_in, "batch_process_fmt(in)") || !check_buffer(b, d_out, "batch_process_fmt(out)")) return -1;
+    const bool in_plain = buffer_is_plain(*d_in), out_plain = buffer_is_plain(*d_out);
+    if (in_plain && out_plain)
+        return r8bgpu_batch_process(b, (const double*) d_in->data, d_in->stride, l, (double*) d_out->data,
+                                    d_out->stride, out_cap);
+    if (l < 0 || l > b->plan->max_in_len) {
+        set_err("batch_process_fmt: l must be in [0, MaxInLen]");
+        return -1;
+    }
+    if (l > 0 && d_in->data == nullptr) {
+        set_err("batch_process_fmt: null input");
+        return -1;
+    }
+    DeviceGuard g(b->device);
+    const Plan& P = *b->plan;
+    const size_t in_cap = (size_t) P.max_in_len;
+    const size_t o_cap = ((size_t) P.max_out_len + 3) & ~(size_t) 3;
+    if (!ensure_staging(b)) return -1;
+    const cudaStream_t st = b->stream;
+    int n = l;
+    if (!P.passthrough) {
+        Schedule saved = b->sched;
+        n = b->sched.advance(l, b->calls);
+        if (n > out_cap || (n > 0 && d_out->data == nullptr)) {
+            b->sched = saved;
+            set_err("batch_process_fmt: output capacity too small for this call");
+            return -1;
+        }
+        if (!upload_fasttiming(b, st)) return -1;
+    } else if (l > out_cap) {
+        set_err("batch_process_fmt: output capacity too small");
+        return -1;
+    }
+    const double* src = (const double*) d_in->data;
+    size_t src_stride = d_in->stride;
+    if (!in_plain) {
+        launch_to_f64(d_in->format, d_in->data, d_in->interleaved != 0, d_in->stride, b->st_in, in_cap, l, b->n_ch,
+                      d_in->scale, st);
+        b->launches++;
+        src = b->st_in;
+        src_stride = in_cap;
+    }
+    double* dst = out_plain ? (double*) d_out->data : b->st_out;
+    const size_t dst_stride = out_plain ? d_out->stride : o_cap;
+    if (P.passthrough) {
+        if (l > 0) cudaMemcpy2DAsync(dst, dst_stride * sizeof(double), src, src_stride * sizeof(double),
+                                     (size_t) l * sizeof(double), (size_t) b->n_ch, cudaMemcpyDeviceToDevice, st);
+    } else {
+        launch_call(b, src, src_stride, l, dst, dst_stride, 0, b->n_ch, st);
+    }
+    if (!out_plain) {
+        launch_from_f64(d_out->format, d_out->data, d_out->interleaved != 0, d_out->stride, b->st_out, o_cap, n, b->n_ch,
+                        d_out->scale, st);
+        b->launches++;
+    }
+    if (!cuda_ok(cudaGetLastError(), "batch_process_fmt: kernel launch")) return -1;
     return n;
 }
 

@@ -6,8 +6,8 @@
 //
 //   k_blockconv   CDSPBlockConvolver::process + CDSPRealFFT fwd/inv + multiplyBlocksZP +
 //                 mirrorInputSpectrum  (CDSPBlockConvolver.h:252-354,606-629; CDSPRealFFT.h:98-385)
-//   k_frac_whole  CDSPFracInterpolator::convolve0<N>      (CDSPFracInterpolator.h:991-1060)
-//   k_frac_poly   CDSPFracInterpolator::convolve2          (CDSPFracInterpolator.h:1069-1179)
+//   k_frac<false> CDSPFracInterpolator::convolve0<N>      (CDSPFracInterpolator.h:991-1060)
+//   k_frac<true>  CDSPFracInterpolator::convolve2          (CDSPFracInterpolator.h:1069-1179)
 //   k_hbup        CDSPHBUpsampler::process / convolveN     (CDSPHBUpsampler.h:674-732, .inc)
 //   k_hbdown      CDSPHBDownsampler::process / convolveN   (CDSPHBDownsampler.h:137-239, .inc)
 //
@@ -202,43 +202,29 @@ void launch_blockconv(const BlockConvParams& p, const SrcView& src, const DstVie
 cudaError_t blockconv_configure() { return cudaSuccess; }
 
 // ------------------------------------------------------------------------------------------
-// Fractional-delay interpolation, whole-number stepping: output j sits at input position
-// j*InStep/OutStep; the fractional part selects one of OutStep precomputed filters.
-__global__ void __launch_bounds__(256) k_frac_whole(FracParams p, SrcView src, DstView dst)
-{
-    const long long j = p.e0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p.e1) return;
-    const int ch = blockIdx.y;
-    const long long pos = j * p.in_step;
-    const long long ip = pos / p.out_step;
-    const int phase = (int) (pos - ip * p.out_step);
-    const double* __restrict__ b = p.bank + (long long) phase * p.flen;
-    const long long x0 = ip - p.fll;
-    double acc = 0.0;
-    for (int i = 0; i < p.flen; i++) acc = fma(__ldg(b + i), src_read(src, ch, x0 + i), acc);
-    dst_write(dst, ch, j, acc);
-}
-
-void launch_frac_whole(const FracParams& p, const SrcView& src, const DstView& dst, int n_ch,
-                       cudaStream_t st)
-{
-    const long long n = p.e1 - p.e0;
-    if (n <= 0 || n_ch <= 0) return;
-    dim3 grid((unsigned) ((n + 255) / 256), (unsigned) n_ch);
-    k_frac_whole<<<grid, 256, 0, st>>>(p, src, dst);
-}
-
-// Non-whole stepping: bank of `fracs` filters, each tap a quadratic in the residual fraction.
-// The timing arithmetic reproduces the reference's IEEE expression order exactly
+// Fractional-delay interpolation.  One block = `tile` consecutive outputs of one channel; the input
+// window they touch is staged once in shared memory (positions are non-decreasing in the output
+// index, so the window is [pos(first) - fll, pos(last) - fll + flen)).
+//
+// Whole-number stepping: output j sits at input position j*InStep/OutStep; the fractional part selects
+// one of OutStep precomputed filters.
+// Non-whole stepping: bank of `fracs` filters, each tap a quadratic in the residual fraction.  The
+// timing arithmetic reproduces the reference's IEEE expression order exactly
 // ((InCounter + InPosShift) * ssr) / dsr -- explicit _rn intrinsics forbid FMA contraction.
-__global__ void __launch_bounds__(256) k_frac_poly(FracParams p, SrcView src, DstView dst)
+template <bool POLY>
+__device__ __forceinline__ void frac_position(const FracParams& p, long long k, long long& ip, int& phase,
+                                              double& fpos)
 {
-    const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    const long long j = p.e0 + k;
-    if (j >= p.e1) return;
-    const int ch = blockIdx.y;
-    long long ip = p.p0;
-    double fpos = p.fpos0;
+    if (!POLY) {
+        const long long pos = (p.e0 + k) * p.in_step;
+        ip = pos / p.out_step;
+        phase = (int) (pos - ip * p.out_step);
+        fpos = 0.0;
+        return;
+    }
+    phase = 0;
+    ip = p.p0;
+    fpos = p.fpos0;
     if (p.pos_dp != nullptr) { // R8B_FASTTIMING: host-walked sequence
         ip = p.p0 + __ldg(p.pos_dp + k);
         fpos = __ldg(p.pos_fpos + k);
@@ -249,27 +235,80 @@ __global__ void __launch_bounds__(256) k_frac_poly(FracParams p, SrcView src, Ds
         ip = p.p0 + (ni - p.in_pos_int0);
         fpos = __dsub_rn(np, (double) ni);
     }
-    double x = __dmul_rn(fpos, (double) p.fracs);
-    const int fti = __double2int_rz(x);
-    x = __dsub_rn(x, (double) fti);
-    const double x2 = __dmul_rn(x, x);
-    const double* __restrict__ b = p.bank + (long long) fti * p.flen * 3;
-    const long long x0 = ip - p.fll;
-    double acc = 0.0;
-    for (int i = 0; i < p.flen; i++) {
-        const double c = fma(__ldg(b + 3 * i + 2), x2, fma(__ldg(b + 3 * i + 1), x, __ldg(b + 3 * i)));
-        acc = fma(c, src_read(src, ch, x0 + i), acc);
+}
+
+template <bool POLY>
+__global__ void __launch_bounds__(256) k_frac(FracParams p, SrcView src, DstView dst, int tile, int cap)
+{
+    extern __shared__ double s_x[];
+    const int ch = blockIdx.y, tid = threadIdx.x;
+    const long long k0 = (long long) blockIdx.x * tile;
+    const int cnt = (int) min((long long) tile, p.e1 - p.e0 - k0);
+    long long ip_lo, ip_hi;
+    int ph;
+    double fp;
+    frac_position<POLY>(p, k0, ip_lo, ph, fp);
+    frac_position<POLY>(p, k0 + cnt - 1, ip_hi, ph, fp);
+    const int len = (int) (ip_hi - ip_lo) + p.flen;
+    if (len > cap) __trap(); // host sizing bug; never silently wrong
+    const long long base = ip_lo - p.fll;
+    for (int i = tid; i < len; i += 256) s_x[i] = src_read(src, ch, base + i);
+    __syncthreads();
+    for (int kk = tid; kk < cnt; kk += 256) {
+        long long ip;
+        frac_position<POLY>(p, k0 + kk, ip, ph, fp);
+        const double* __restrict__ xs = s_x + (int) (ip - ip_lo);
+        double acc = 0.0;
+        if (!POLY) {
+            const double* __restrict__ b = p.bank + (long long) ph * p.flen;
+            for (int i = 0; i < p.flen; i++) acc = fma(__ldg(b + i), xs[i], acc);
+        } else {
+            double x = __dmul_rn(fp, (double) p.fracs);
+            const int fti = __double2int_rz(x);
+            x = __dsub_rn(x, (double) fti);
+            const double x2 = __dmul_rn(x, x);
+            const double* __restrict__ b = p.bank + (long long) fti * p.flen * 3;
+            for (int i = 0; i < p.flen; i++) {
+                const double c = fma(__ldg(b + 3 * i + 2), x2, fma(__ldg(b + 3 * i + 1), x, __ldg(b + 3 * i)));
+                acc = fma(c, xs[i], acc);
+            }
+        }
+        dst_write(dst, ch, p.e0 + k0 + kk, acc);
     }
-    dst_write(dst, ch, j, acc);
+}
+
+// Tile size such that the staged window fits FRAC_CAP doubles for a given input/output rate ratio.
+// Kept small on purpose: the filter bank is read through L1 (one row per lane), and shared memory carved
+// out for the window is L1 capacity lost to the bank.
+constexpr int FRAC_CAP = 1536; // 12 KB
+static int frac_tile(double in_per_out, int flen)
+{
+    int tile = 1024;
+    while (tile > 32 && (double) tile * in_per_out + flen + 4 > (double) FRAC_CAP) tile >>= 1;
+    return tile;
+}
+
+template <bool POLY>
+static void launch_frac(const FracParams& p, double in_per_out, const SrcView& src, const DstView& dst,
+                        int n_ch, cudaStream_t st)
+{
+    const long long n = p.e1 - p.e0;
+    if (n <= 0 || n_ch <= 0) return;
+    const int tile = frac_tile(in_per_out, p.flen);
+    dim3 grid((unsigned) ((n + tile - 1) / tile), (unsigned) n_ch);
+    k_frac<POLY><<<grid, 256, FRAC_CAP * sizeof(double), st>>>(p, src, dst, tile, FRAC_CAP);
+}
+
+void launch_frac_whole(const FracParams& p, const SrcView& src, const DstView& dst, int n_ch,
+                       cudaStream_t st)
+{
+    launch_frac<false>(p, (double) p.in_step / (double) p.out_step, src, dst, n_ch, st);
 }
 
 void launch_frac_poly(const FracParams& p, const SrcView& src, const DstView& dst, int n_ch,
                       cudaStream_t st)
 {
-    const long long n = p.e1 - p.e0;
-    if (n <= 0 || n_ch <= 0) return;
-    dim3 grid((unsigned) ((n + 255) / 256), (unsigned) n_ch);
-    k_frac_poly<<<grid, 256, 0, st>>>(p, src, dst);
+    launch_frac<true>(p, p.ssr / p.dsr, src, dst, n_ch, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -296,23 +335,42 @@ void launch_hbup(const HbParams& p, const SrcView& src, const DstView& dst, int 
 }
 
 // Half-band 2x decimator (gain 2, compensated by the following low-pass's gain).
+// One block = HBD_TILE outputs of one channel; its input window is staged once in shared memory,
+// split into the even (centre) and odd (tapped) samples so that consecutive lanes read consecutive
+// words.  Summation order per output: centre, then taps k = 0..T-1 on (x[c+1+2k] + x[c-1-2k]).
+constexpr int HBD_TILE = 1024;
 __global__ void __launch_bounds__(256) k_hbdown(HbParams p, SrcView src, DstView dst)
 {
-    const long long m = p.e0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= p.e1) return;
-    const int ch = blockIdx.y;
-    const long long c = 2 * m;
-    double acc = src_read(src, ch, c);
-    for (int k = 0; k < p.ntaps; k++)
-        acc = fma(p.taps[k], src_read(src, ch, c + 1 + 2 * k) + src_read(src, ch, c - 1 - 2 * k), acc);
-    dst_write(dst, ch, m, acc);
+    __shared__ double s_even[HBD_TILE];
+    __shared__ double s_odd[HBD_TILE + 2 * 14];
+    const int ch = blockIdx.y, tid = threadIdx.x, T = p.ntaps;
+    const long long m0 = p.e0 + (long long) blockIdx.x * HBD_TILE;
+    const int cnt = (int) min((long long) HBD_TILE, p.e1 - m0);
+    // s_odd[i] = x[2*(m0 - T + i) + 1], i < cnt + 2T - 1 ; s_even[i] = x[2*(m0 + i)], i < cnt
+    const long long n0 = 2 * (m0 - T) + 1;
+    const int n_in = 2 * (cnt + 2 * T - 1) - 1;
+    for (int i = tid; i < n_in; i += 256) {
+        const double x = src_read(src, ch, n0 + i);
+        if (i & 1) {
+            const int e = (i + 1) / 2 - T; // n0+i = 2*(m0-T) + i+1
+            if (e >= 0 && e < cnt) s_even[e] = x;
+        } else {
+            s_odd[i >> 1] = x;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < cnt; i += 256) {
+        double acc = s_even[i];
+        for (int k = 0; k < T; k++) acc = fma(p.taps[k], s_odd[i + T + k] + s_odd[i + T - 1 - k], acc);
+        dst_write(dst, ch, m0 + i, acc);
+    }
 }
 
 void launch_hbdown(const HbParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
 {
     const long long n = p.e1 - p.e0;
     if (n <= 0 || n_ch <= 0) return;
-    dim3 grid((unsigned) ((n + 255) / 256), (unsigned) n_ch);
+    dim3 grid((unsigned) ((n + HBD_TILE - 1) / HBD_TILE), (unsigned) n_ch);
     k_hbdown<<<grid, 256, 0, st>>>(p, src, dst);
 }
 

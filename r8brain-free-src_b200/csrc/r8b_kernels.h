@@ -139,4 +139,13 @@ void launch_save_tail(const double* cur, long long cur_stride, long long cur_bas
                       long long n1, double* ring, long long ring_stride, long long ring_mask, int n_ch,
                       cudaStream_t st);
 
+// Caller-side sample formats (r8b_format.cu); values match r8bgpu_sample_format in include/r8bgpu.h.
+enum { FMT_F64 = 0, FMT_F32 = 1, FMT_S16 = 2, FMT_S24 = 3, FMT_S32 = 4 };
+__host__ __device__ int format_bytes(int fmt); // 0: unknown format
+// raw (any format; planar: channel c at c*raw_stride, interleaved: frame f at f*raw_stride) <-> planar fp64
+bool launch_to_f64(int fmt, const void* raw, bool interleaved, size_t raw_stride, double* f64, size_t f64_stride,
+                   int n, int n_ch, double scale, cudaStream_t st);
+bool launch_from_f64(int fmt, void* raw, bool interleaved, size_t raw_stride, const double* f64, size_t f64_stride,
+                     int n, int n_ch, double scale, cudaStream_t st);
+
 } // namespace r8bgpu
