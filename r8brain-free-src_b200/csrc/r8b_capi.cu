@@ -218,7 +218,7 @@ struct r8bgpu_batch {
     {
         DeviceGuard g(device);
         if (prof != nullptr) {
-            unsigned long long h[8] = {};
+            unsigned long long h[10] = {};
             cudaDeviceSynchronize();
             cudaMemcpy(h, prof, sizeof h, cudaMemcpyDeviceToHost);
             static const char* nm[8] = {"gather+fwd1", "fwd2", "fwd3", "C(split*G)", "inv1", "inv2", "inv3+ystore", "interp"};
@@ -228,6 +228,9 @@ struct r8bgpu_batch {
             for (int i = 0; i < 8; i++)
                 fprintf(stderr, "  %-12s %9.0f  (%4.1f %%)\n", nm[i], prof_ctas ? (double) h[i] / prof_ctas : 0.0,
                         tot ? 100.0 * h[i] / tot : 0.0);
+            if (h[8] + h[9] > 0)
+                fprintf(stderr, "  order-2 bank, clk per CTA: 4-output groups %.0f, queued single outputs %.0f\n",
+                        (double) h[8] / prof_ctas, (double) h[9] / prof_ctas);
             cudaFree(prof);
         }
         for (auto& d : dev) {
@@ -858,9 +861,34 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.p0 = fc.p0;
             p.pos_dp = fd.ft_dp;
             p.pos_fpos = fd.ft_fpos;
+            if (p.mode == 1 && (p.flen & 1) == 0 && !getenv("R8BGPU_BANK_GLOBAL")) {
+                // bank-row drift per output, in rows: frac(ssr/dsr) * fracs upward, or (1 - frac) * fracs downward
+                const double ratio = p.ssr / p.dsr, fr = ratio - floor(ratio);
+                const double outs = 2.0 * p.span / ratio + 4.0; // outputs one tile pair can own
+                const int row_words = 6 * p.flen; // 32-bit words per bank row
+                p.poly_row_stride = 3 * p.flen + ((row_words % 8) == 4 ? 0 : 2);
+                const int cap = (224 * 1024 - fused_smem_bytes(0) - fused_poly_queue_bytes()) /
+                                (p.poly_row_stride * (int) sizeof(double));
+                const double up = fr * p.fracs * outs + 4.0, dn = (1.0 - fr) * p.fracs * outs + 4.0;
+                const double need = up < dn ? up : dn;
+                const int chunks = (int) ceil(need / cap);
+                if (cap >= 8 && chunks <= 4) { // more pieces than that: the rows are not a short run, read them from L2
+                    p.poly_dir = up < dn ? 1 : -1;
+                    p.poly_rows_cap = cap;
+                    p.poly_chunks = chunks < 1 ? 1 : chunks;
+                    const long long nn = llround(ratio);
+                    if (nn >= 1 && nn <= 3 && !getenv("R8BGPU_POLY_SINGLE")) {
+                        // four consecutive outputs per thread: lanes step by 4*nn samples through the tile -> padded
+                        // y layout (i + (i >> 4), the only padding the tile buffers have room for)
+                        p.poly_n = (int) nn;
+                        p.ysh = 4;
+                    }
+                }
+            }
+            if (p.poly_chunks < 1) p.poly_chunks = 1;
             if (b->prof == nullptr && getenv("R8BGPU_PROFILE")) {
-                cudaMalloc(&b->prof, 8 * sizeof(unsigned long long));
-                cudaMemset(b->prof, 0, 8 * sizeof(unsigned long long));
+                cudaMalloc(&b->prof, 10 * sizeof(unsigned long long));
+                cudaMemset(b->prof, 0, 10 * sizeof(unsigned long long));
             }
             p.prof = b->prof;
             if (const char* e = getenv("R8BGPU_DEBUG")) p.debug = atoi(e);

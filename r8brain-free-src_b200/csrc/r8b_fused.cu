@@ -22,6 +22,7 @@
 #include <climits>
 
 #include "r8b_fft.cuh"
+#include "r8b_interp.cuh"
 
 namespace r8bgpu {
 
@@ -314,6 +315,245 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
 } // namespace
 
 // MODE 0: whole stepping, MODE 1: order-2 polynomial bank.
+// ---- order-2 bank (non-whole stepping) helpers ------------------------------------------------
+// Position and fraction of output k of this call; the reference's IEEE expression order
+// ((InCounter + InPosShift) * ssr) / dsr (CDSPFracInterpolator.h:1161-1166), or the host-walked
+// R8B_FASTTIMING sequence.
+__device__ __forceinline__ void poly_position(const FusedParams& p, long long k, long long& ip, double& fpos)
+{
+    ip = p.p0;
+    fpos = p.fpos0;
+    if (p.pos_dp != nullptr) {
+        ip = p.p0 + __ldg(p.pos_dp + k);
+        fpos = __ldg(p.pos_fpos + k);
+    } else if (k > 0) {
+        const int ic = p.in_counter0 + (int) k;
+        const double np = __ddiv_rn(__dmul_rn(__dadd_rn((double) ic, p.in_pos_shift), p.ssr), p.dsr);
+        const int ni = __double2int_rz(np);
+        ip = p.p0 + (ni - p.in_pos_int0);
+        fpos = __dsub_rn(np, (double) ni);
+    }
+}
+
+// First k in [0, nk] whose position is >= lim (positions are non-decreasing in k).
+__device__ __forceinline__ long long poly_first_k(const FusedParams& p, long long lim, long long nk)
+{
+    auto pos = [&](long long k) {
+        long long ip;
+        double f;
+        poly_position(p, k, ip, f);
+        return ip;
+    };
+    if (p.pos_dp != nullptr) { // table: binary search
+        long long lo = 0, hi = nk;
+        while (lo < hi) {
+            const long long mid = lo + (hi - lo) / 2;
+            if (pos(mid) >= lim) hi = mid;
+            else lo = mid + 1;
+        }
+        return lo;
+    }
+    // closed form: invert the timing expression, then settle on the exact integer with the exact expression
+    const double t = (double) (lim - p.p0 + p.in_pos_int0);
+    double est = ceil(t * p.dsr / p.ssr - p.in_pos_shift - (double) p.in_counter0);
+    long long k = est < 0.0 ? 0 : (est > (double) nk ? nk : (long long) est);
+    while (k > 0 && pos(k - 1) >= lim) k--;
+    while (k < nk && pos(k) < lim) k++;
+    return k;
+}
+
+// Circular run of bank rows used by outputs [k_lo, k_hi): first row and number of rows to stage (0 = none).
+// One row of margin on either side: rounding of the fraction may step past the end rows.  Rows outside the
+// staged run are always read from global memory, so this is an optimisation only.
+__device__ __forceinline__ void poly_rows_for(const FusedParams& p, long long k_lo, long long k_hi, int& r_lo, int& n_st)
+{
+    r_lo = 0;
+    n_st = 0;
+    if (p.poly_dir == 0 || p.poly_rows_cap <= 0 || k_hi <= k_lo) return;
+    long long ip;
+    double f0, f1;
+    poly_position(p, k_lo, ip, f0);
+    poly_position(p, k_hi - 1, ip, f1);
+    int ra = __double2int_rz(__dmul_rn(f0, (double) p.fracs));
+    int rb = __double2int_rz(__dmul_rn(f1, (double) p.fracs));
+    if (ra >= p.fracs) ra = p.fracs - 1;
+    if (rb >= p.fracs) rb = p.fracs - 1;
+    const int first = p.poly_dir > 0 ? ra : rb, last = p.poly_dir > 0 ? rb : ra;
+    int cnt = last - first;
+    if (cnt < 0) cnt += p.fracs;
+    cnt += 3;
+    r_lo = first > 0 ? first - 1 : p.fracs - 1;
+    n_st = cnt < p.poly_rows_cap ? cnt : p.poly_rows_cap;
+    if (n_st > p.fracs) n_st = p.fracs;
+}
+
+// Outputs [ka, kb) of a pair are processed in p.poly_chunks equal pieces, each with its own staged rows.
+__device__ __forceinline__ long long poly_chunk_start(long long ka, long long kb, int c, int n_chunks)
+{
+    return ka + (kb - ka) * c / n_chunks;
+}
+
+// One thread, at kernel start: the pair's output range [ka, kb) -> s_j, rows of chunk 0 -> s_i[0..1].
+__device__ __forceinline__ void poly_prepare(const FusedParams& p, long long A0, long long B1, int* s_j, int* s_i)
+{
+    const long long nk = p.e1 - p.e0;
+    const long long ka = poly_first_k(p, A0, nk), kb = poly_first_k(p, B1, nk);
+    s_j[0] = (int) ka;
+    s_j[1] = (int) kb;
+    int r_lo, n_st;
+    poly_rows_for(p, ka, poly_chunk_start(ka, kb, 1, p.poly_chunks), r_lo, n_st);
+    s_i[0] = r_lo;
+    s_i[1] = n_st;
+}
+
+// Copy rows (r_lo + s) mod fracs, s < n_st, into shared memory with threads t0, t0 + nthr, ...
+__device__ __forceinline__ void poly_stage_rows(const FusedParams& p, double* sbank, int r_lo, int n_st, int t0, int nthr)
+{
+    const int rl2 = (3 * p.flen) >> 1; // double2 per row (flen is even whenever rows are staged)
+    double2* sb2 = reinterpret_cast<double2*>(sbank);
+    const double2* gb2 = reinterpret_cast<const double2*>(p.bank);
+    for (int i = t0; i < n_st * rl2; i += nthr) {
+        const int sl = i / rl2;
+        int row = r_lo + sl;
+        if (row >= p.fracs) row -= p.fracs;
+        sb2[sl * (p.poly_row_stride >> 1) + (i - sl * rl2)] = __ldg(gb2 + (long long) row * rl2 + (i - sl * rl2));
+    }
+}
+
+// ---- order-2 bank: the output loop ------------------------------------------------------------
+constexpr int POLY_QUEUE = 1024; // deferred outputs per chunk (4 KB of dynamic shared memory behind the staged rows)
+int fused_poly_queue_bytes() { return POLY_QUEUE * (int) sizeof(int); }
+
+struct PolyCtx {
+    const double* smd;    // dynamic shared memory as doubles: tile b's y at 0, tile a's y at 2*FPL
+    const double* sbank;  // staged rows: slot s holds row (r_lo + s) mod fracs
+    int r_lo, n_st;
+    long long ya0, yb0;   // absolute 2x index of y element 0 of tile a / tile b
+    long long bsel;       // windows starting at or after this position use tile b
+    int ch;
+    int* queue;           // outputs deferred to the one-output-per-lane pass (POLY_QUEUE entries)
+    int* q_count;
+};
+
+struct PolyOut {          // everything one output needs
+    double x, x2;
+    int fti, yi;          // bank row; logical index of the window start in its tile buffer
+    bool use_b, ok;
+};
+
+template <bool PADV>
+__device__ __forceinline__ PolyOut poly_output(const FusedParams& p, const PolyCtx& cx, long long k)
+{
+    PolyOut o;
+    long long ip;
+    double fpos;
+    poly_position(p, k, ip, fpos);
+    double x = __dmul_rn(fpos, (double) p.fracs);
+    o.fti = __double2int_rz(x);
+    x = __dsub_rn(x, (double) o.fti);
+    o.x = x;
+    o.x2 = __dmul_rn(x, x);
+    const long long ws = ip - p.fll;
+    o.use_b = ws >= cx.bsel;
+    o.yi = (int) (ws - (o.use_b ? cx.yb0 : cx.ya0));
+    o.ok = o.yi >= 0 && o.yi + p.flen <= 2 * FM; // always true for owned outputs
+    return o;
+}
+
+template <bool PADV>
+__device__ __forceinline__ double poly_single(const FusedParams& p, const PolyCtx& cx, const PolyOut& o)
+{
+    const double* yb = cx.smd + (o.use_b ? 0 : 2 * FPL);
+    const int yi = o.yi, ysh = p.ysh;
+    auto y = [=](int i) { return PADV ? yb[ylay(yi + i, ysh)] : yb[yi + i]; };
+    const int rowlen = 3 * p.flen;
+    int slot = o.fti - cx.r_lo;
+    if (slot < 0) slot += p.fracs;
+    if (slot < cx.n_st && o.fti < p.fracs)
+        return poly_row_dot<true>(cx.sbank + slot * p.poly_row_stride, p.flen, o.x, o.x2, y);
+    return poly_row_dot<false>(p.bank + (long long) o.fti * rowlen, p.flen, o.x, o.x2, y);
+}
+
+// Outputs [k_lo, k_hi) of one chunk.  N > 0: threads take four consecutive outputs; when these share a staged
+// bank row and their windows start exactly N samples apart (the steady state of a slowly drifting ratio
+// ~ N) the coefficient loads are shared (poly_block4), otherwise each output goes the single-output way.
+// N == 0: one output per thread.
+template <int N, bool PADV>
+__device__ __forceinline__ void poly_outputs(const FusedParams& p, const DstView& dst, const PolyCtx& cx, int k_lo, int k_hi,
+                                             int tid)
+{
+    if (N == 0) {
+        for (int k = k_lo + tid; k < k_hi; k += FNT) {
+            const PolyOut o = poly_output<PADV>(p, cx, k);
+            if (!o.ok) continue;
+            dst_write_f(dst, cx.ch, p.e0 + k, poly_single<PADV>(p, cx, o));
+        }
+        return;
+    }
+    // Groups that do not qualify (the bank row changes inside the group, a tile boundary, the last few outputs)
+    // are not computed in place -- a warp would serialise its few slow lanes behind the fast ones on every
+    // pass -- but queued in shared memory and computed afterwards one output per lane, all lanes busy.
+    constexpr int NN = N > 0 ? N : 1;
+#ifdef R8BGPU_PHASE_TIMERS
+    long long tq0 = clock64();
+#endif
+    for (int k = k_lo + 4 * tid; k < k_hi; k += 4 * FNT) {
+        PolyOut o[4];
+        const int nv = min(4, k_hi - k);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (r < nv) o[r] = poly_output<PADV>(p, cx, k + r);
+        bool fast = nv == 4 && o[0].ok && o[3].ok;
+        if (fast) {
+#pragma unroll
+            for (int r = 1; r < 4; r++)
+                fast = fast && o[r].fti == o[0].fti && o[r].use_b == o[0].use_b && o[r].yi == o[0].yi + NN * r;
+        }
+        int slot = o[0].fti - cx.r_lo;
+        if (slot < 0) slot += p.fracs;
+        fast = fast && slot < cx.n_st && o[0].fti < p.fracs;
+        if (fast) {
+            const double* yb = cx.smd + (o[0].use_b ? 0 : 2 * FPL);
+            const int yi = o[0].yi, ysh = p.ysh;
+            auto y = [=](int j) { return PADV ? yb[ylay(yi + j, ysh)] : yb[yi + j]; };
+            const double xs[4] = {o[0].x, o[1].x, o[2].x, o[3].x};
+            const double x2s[4] = {o[0].x2, o[1].x2, o[2].x2, o[3].x2};
+            double acc[4];
+            poly_block4<NN>(cx.sbank + slot * p.poly_row_stride, p.flen, xs, x2s, y, acc);
+#pragma unroll
+            for (int r = 0; r < 4; r++) dst_write_f(dst, cx.ch, p.e0 + k + r, acc[r]);
+        } else {
+            const int at = atomicAdd(cx.q_count, nv);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                if (r >= nv) continue;
+                if (at + r < POLY_QUEUE) cx.queue[at + r] = k + r;
+                else if (o[r].ok) dst_write_f(dst, cx.ch, p.e0 + k + r, poly_single<PADV>(p, cx, o[r])); // queue full
+            }
+        }
+    }
+    __syncthreads();
+#ifdef R8BGPU_PHASE_TIMERS
+    if (p.prof != nullptr && tid == 0) {
+        const long long t = clock64();
+        atomicAdd(&p.prof[8], (unsigned long long) (t - tq0));
+        tq0 = t;
+    }
+#endif
+    const int nq = min(*cx.q_count, POLY_QUEUE);
+    for (int i = tid; i < nq; i += FNT) {
+        const int k = cx.queue[i];
+        const PolyOut o = poly_output<PADV>(p, cx, k);
+        if (o.ok) dst_write_f(dst, cx.ch, p.e0 + k, poly_single<PADV>(p, cx, o));
+    }
+#ifdef R8BGPU_PHASE_TIMERS
+    if (p.prof != nullptr) {
+        __syncthreads();
+        if (tid == 0) atomicAdd(&p.prof[9], (unsigned long long) (clock64() - tq0));
+    }
+#endif
+}
+
 template <int MODE, int IRV, bool PADV, bool BANKV>
 __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src, DstView dst)
 {
@@ -325,6 +565,7 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     double2* twf = tw2 + 256;          // tw1t[q*16+r] = W_M^(r q)
     double* sbank = reinterpret_cast<double*>(twf + 256); // whole-step bank (if it fits)
     __shared__ int s_j[2];
+    __shared__ int s_q;
     __shared__ int s_i[8];
     __shared__ double* s_o;
     __shared__ int s_goff[192];
@@ -370,8 +611,12 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
             const long long bsel0 = has_b ? B0 - p.yl : LLONG_MAX;
             interp_prepare(p, dst, ch, 2 * wa, 2 * wb, bsel0, A0, B1, s_i, &s_o);
         }
+    } else if (tid == 511) {
+        poly_prepare(p, A0, B1, s_j, s_i);
     }
     __syncthreads();
+    // threads idle during the forward transform stage the bank rows of the pair's first chunk
+    if (MODE == 1 && tid >= 256) poly_stage_rows(p, sbank, s_i[0], s_i[1], tid - 256, 256);
 
     // optional phase timing: build with R8BGPU_PHASE_TIMERS=1 (adds -DR8BGPU_PHASE_TIMERS) and run with
     // R8BGPU_PROFILE=1; thread 0 accumulates clock64() deltas per phase.  Compiled out by default: the live
@@ -477,11 +722,8 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     __syncthreads();
     R8B_TICK(6)
 
-    const double* ya = reinterpret_cast<const double*>(bufB);
-    const double* ybuf_b = reinterpret_cast<const double*>(bufA);
     const long long ya0 = 2 * wa, yb0 = 2 * wb;   // absolute 2x index of local double 0
     const long long bsel = has_b ? B0 - p.yl : LLONG_MAX; // windows starting at or after this use tile b
-    constexpr int YMAX = 2 * FM;                  // doubles per tile buffer (before layout padding)
 
     if (MODE == 0) {
         const double* smd = reinterpret_cast<const double*>(smem);
@@ -490,60 +732,36 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
                                        p.stage_off > 0 ? reinterpret_cast<double*>(smem) + p.stage_off : nullptr, s_i, &s_o,
                                        s_goff, tid);
     } else {
-        // order-2 bank: output k of this call (k >= 0) sits at (p_k, fpos_k); find the pair's k range
-        if (tid == 0) {
-            // p_k is non-decreasing in k: binary search the first k with p_k >= A0 and with p_k >= B1
-            long long lim[2] = {A0, B1};
-            const long long nk = p.e1 - p.e0;
-            for (int t = 0; t < 2; t++) {
-                long long lo = 0, hi = nk; // answer in [0, nk]
-                while (lo < hi) {
-                    const long long mid = lo + (hi - lo) / 2;
-                    long long pk = p.p0;
-                    if (p.pos_dp != nullptr) {
-                        pk = mid < nk ? p.p0 + __ldg(p.pos_dp + mid) : 0x7fffffffffffffffLL;
-                    } else if (mid > 0) {
-                        const int ic = p.in_counter0 + (int) mid;
-                        const double np = __ddiv_rn(__dmul_rn(__dadd_rn((double) ic, p.in_pos_shift), p.ssr), p.dsr);
-                        pk = p.p0 + (__double2int_rz(np) - p.in_pos_int0);
-                    }
-                    if (pk >= lim[t]) hi = mid;
-                    else lo = mid + 1;
-                }
-                s_j[t] = (int) lo;
-            }
-        }
-        __syncthreads();
+        // order-2 bank: output k of this call (k >= 0) sits at (p_k, fpos_k); the pair owns k in [ka, kb)
+        // (found by poly_prepare at kernel start)
         const int ka = s_j[0], kb = s_j[1];
-        for (int k = ka + tid; k < kb; k += FNT) {
-            long long ip = p.p0;
-            double fpos = p.fpos0;
-            if (p.pos_dp != nullptr) { // R8B_FASTTIMING: host-walked sequence
-                ip = p.p0 + __ldg(p.pos_dp + k);
-                fpos = __ldg(p.pos_fpos + k);
-            } else if (k > 0) {
-                const int ic = p.in_counter0 + k;
-                const double np = __ddiv_rn(__dmul_rn(__dadd_rn((double) ic, p.in_pos_shift), p.ssr), p.dsr);
-                const int ni = __double2int_rz(np);
-                ip = p.p0 + (ni - p.in_pos_int0);
-                fpos = __dsub_rn(np, (double) ni);
+        int r_lo = s_i[0], n_st = s_i[1];
+        const double* smd1 = reinterpret_cast<const double*>(smem);
+        for (int c = 0; c < p.poly_chunks; c++) {
+            const int k_lo = (int) poly_chunk_start(ka, kb, c, p.poly_chunks);
+            const int k_hi = (int) poly_chunk_start(ka, kb, c + 1, p.poly_chunks);
+            __syncthreads(); // everyone is done with the previous chunk's rows and queue
+            if (tid == 0) s_q = 0;
+            if (c > 0) { // next run of rows: every thread derives the same (r_lo, n_st); all threads copy
+                poly_rows_for(p, k_lo, k_hi, r_lo, n_st);
+                poly_stage_rows(p, sbank, r_lo, n_st, tid, FNT);
             }
-            double x = __dmul_rn(fpos, (double) p.fracs);
-            const int fti = __double2int_rz(x);
-            x = __dsub_rn(x, (double) fti);
-            const double x2 = __dmul_rn(x, x);
-            const double* __restrict__ b = p.bank + (long long) fti * p.flen * 3;
-            const long long ws = ip - p.fll;
-            const bool use_b = ws >= bsel;
-            const double* yp = use_b ? ybuf_b : ya;
-            const int yi = (int) (ws - (use_b ? yb0 : ya0));
-            if (yi < 0 || yi + p.flen > YMAX) continue; // cannot happen for owned outputs
-            double acc = 0.0;
-            for (int i = 0; i < p.flen; i++) {
-                const double c = fma(__ldg(b + 3 * i + 2), x2, fma(__ldg(b + 3 * i + 1), x, __ldg(b + 3 * i)));
-                acc = fma(c, yp[ylay(yi + i, p.ysh)], acc);
-            }
-            dst_write_f(dst, ch, p.e0 + k, acc);
+            __syncthreads();
+            PolyCtx cx;
+            cx.smd = smd1;
+            cx.sbank = sbank;
+            cx.r_lo = r_lo;
+            cx.n_st = n_st;
+            cx.ya0 = ya0;
+            cx.yb0 = yb0;
+            cx.bsel = bsel;
+            cx.ch = ch;
+            cx.queue = reinterpret_cast<int*>(sbank + (size_t) p.poly_rows_cap * p.poly_row_stride);
+            cx.q_count = &s_q;
+            if (p.poly_n == 2) poly_outputs<2, PADV>(p, dst, cx, k_lo, k_hi, tid);
+            else if (p.poly_n == 1) poly_outputs<1, PADV>(p, dst, cx, k_lo, k_hi, tid);
+            else if (p.poly_n == 3) poly_outputs<3, PADV>(p, dst, cx, k_lo, k_hi, tid);
+            else poly_outputs<0, PADV>(p, dst, cx, k_lo, k_hi, tid);
         }
     }
 #ifdef R8BGPU_PHASE_TIMERS
@@ -584,7 +802,10 @@ void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& ds
     int smem = fused_smem_bytes((p.mode == 0 && p.bank_in_smem) ? p.gbank_smem_len : 0);
     if (p.mode == 0 && p.stage_off > 0) smem = (p.stage_off + fused_stage_doubles()) * (int) sizeof(double);
     if (p.mode != 0) {
-        launch_inst<1, 8, false, false>(p, src, dst, n_ch, smem, st);
+        smem = fused_smem_bytes(0) +
+               (p.poly_dir != 0 ? p.poly_rows_cap * p.poly_row_stride * (int) sizeof(double) + fused_poly_queue_bytes() : 0);
+        if (p.ysh != 31) launch_inst<1, 8, true, false>(p, src, dst, n_ch, smem, st);
+        else launch_inst<1, 8, false, false>(p, src, dst, n_ch, smem, st);
         return;
     }
     const bool pad = p.ysh != 31, bs = p.bank_in_smem != 0;

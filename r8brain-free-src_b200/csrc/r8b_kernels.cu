@@ -17,6 +17,7 @@
 #include <climits>
 
 #include "r8b_fft.cuh"
+#include "r8b_interp.cuh"
 
 namespace r8bgpu {
 
@@ -267,11 +268,7 @@ __global__ void __launch_bounds__(256) k_frac(FracParams p, SrcView src, DstView
             const int fti = __double2int_rz(x);
             x = __dsub_rn(x, (double) fti);
             const double x2 = __dmul_rn(x, x);
-            const double* __restrict__ b = p.bank + (long long) fti * p.flen * 3;
-            for (int i = 0; i < p.flen; i++) {
-                const double c = fma(__ldg(b + 3 * i + 2), x2, fma(__ldg(b + 3 * i + 1), x, __ldg(b + 3 * i)));
-                acc = fma(c, xs[i], acc);
-            }
+            acc = poly_row_dot<false>(p.bank + (long long) fti * p.flen * 3, p.flen, x, x2, [=](int i) { return xs[i]; });
         }
         dst_write(dst, ch, p.e0 + k0 + kk, acc);
     }

@@ -116,11 +116,20 @@ struct FusedParams {
     long long p0;
     const int* pos_dp;       // R8B_FASTTIMING tables (else nullptr)
     const double* pos_fpos;
+    // order-2 bank: when the bank row index drifts slowly and monotonically (mod fracs) with the output index,
+    // the rows a tile pair needs are a short circular run that is staged in shared memory
+    int poly_dir;            // +1 rows ascend with k, -1 descend, 0 no staging
+    int poly_rows_cap;       // rows of shared memory available for the run
+    int poly_row_stride;     // doubles between staged rows: 3*flen padded so that consecutive rows start 4 (mod 8)
+                             // banks apart -- lanes that sit on different rows then load without bank conflicts
+    int poly_n;              // > 0: input positions advance by ~poly_n per output; threads take 4 consecutive outputs
+    int poly_chunks;         // a pair's outputs are processed in this many pieces, each with its own run (>= 1)
 };
 int fused_smem_bytes(int bank_doubles_in_smem);
 int fused_max_span(int lg, int yl, int yr);
 int fused_stage_doubles();
 int fused_fixed_doubles();
+int fused_poly_queue_bytes();
 void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st);
 
 int blockconv_smem_bytes(int fft_log2, int up);

@@ -288,3 +288,14 @@ def test_tiny_blocks_and_many_channels(pkg, ref):
         assert len(yr) == y.shape[1]
         m, rr = ou.parity_metrics(y[c], yr)
         assert m <= MAX_TOL and rr <= RMS_TOL
+
+
+@pytest.mark.parametrize("src,dst", [
+    (48000.0, 48001.0),     # order-2 bank, rows drift DOWNWARD slowly (staged run, poly_dir = -1)
+    (48000.0, 47990.0),     # upward drift fast enough to need several staged chunks per tile pair
+    (44100.0, 48001.3),     # rows jump all over the bank: nothing staged, rows read from global memory
+    (50000.0, 49999.5),     # very slow drift: one row serves many outputs, wrap-around of the row index
+])
+def test_poly_bank_row_staging(pkg, ref, src, dst):
+    ys, yr = run_both(pkg, ref, src, dst, [8192] * 5 + [333, 8192, 5], n_ch=2, max_in=8192)
+    check(ys, yr)
