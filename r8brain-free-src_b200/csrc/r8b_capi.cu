@@ -537,9 +537,10 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                     {
                         const int g8 = (s.out_step + 7) / 8, g10 = (s.out_step + 9) / 10;
                         const int c8 = ((g8 + 15) / 16) * 8, c10 = ((g10 + 15) / 16) * 10;
-                        (void) c8;
-                        (void) c10; // measured: the 10-phase variant spills registers and is ~4 % slower
-                                    // (2.10 vs 2.02 ms per step on cfg 2) despite the even task split
+                        // measured: the 10-phase variant spills registers; where 8-phase groups can start every call
+                        // on a 64-byte output boundary (out_step % 8 == 0: cfg 2) it loses by ~4 % (2.10 vs 2.02 ms)
+                        // despite the even task split, elsewhere the split wins (cfg 3, out_step 147: 1.88 vs 1.98 ms)
+                        if (s.out_step % 8 != 0 && c10 < c8) ir = 10;
                         if (const char* e = getenv("R8BGPU_IR")) ir = atoi(e) == 10 ? 10 : 8;
                     }
                     const int ng = (s.out_step + ir - 1) / ir;
