@@ -48,6 +48,7 @@ def build(force=False, verbose=False):
             return LIB  # GPU box without a toolchain: use the prebuilt library
         raise RuntimeError("nvcc not found and no prebuilt libr8bgpu.so present")
     extra = ["-DR8BGPU_PHASE_TIMERS"] if os.environ.get("R8BGPU_PHASE_TIMERS") else []
+    extra += os.environ.get("R8BGPU_EXTRA_DEFS", "").split()  # experiments, e.g. "-DR8BGPU_HB_NT=512 -DR8BGPU_HB_MINB=2"
     cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")

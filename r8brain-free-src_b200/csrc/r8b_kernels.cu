@@ -401,6 +401,10 @@ void launch_save_tail(const double* cur, long long cur_stride, long long cur_bas
 // stream s0 (plus the halo the taps reach back/forward through all stages) and produces the
 // corresponding w * 2^c samples of s_c.
 //   s_{k+1}[2n] = s_k[n];  s_{k+1}[2n+1] = sum_j f_k[j] * (s_k[n-j] + s_k[n+1+j]);  s_k[<0] = 0.
+#ifndef R8BGPU_HB_NT
+#define R8BGPU_HB_NT 256
+#endif
+constexpr int HB_NT = R8BGPU_HB_NT;
 __device__ __forceinline__ int hb_pad(int i) { return i + (i >> 2); }
 
 // One cascade stage for a CTA: every thread produces 4 consecutive input positions (8 outputs) from a
@@ -431,7 +435,7 @@ __device__ __forceinline__ void hb_stage(const double* __restrict__ in, long lon
     const bool neg = (L < 0); // stream values at negative indices are zeros, not filter outputs
     double* const obase = (last && dst.mask == -1) ? dst.ptr + (long long) ch * dst.stride + (L - dst.base) : nullptr;
     const bool vec_ok = obase != nullptr && ((reinterpret_cast<unsigned long long>(obase) & 15) == 0) && cj == 0;
-    for (int q = tid; q < n_quads; q += 256) {
+    for (int q = tid; q < n_quads; q += HB_NT) {
         double w[2 * T + 3];
 #pragma unroll
         for (int i = 0; i < 2 * T + 3; i++) {
@@ -476,8 +480,13 @@ __device__ __forceinline__ void hb_stage(const double* __restrict__ in, long lon
     }
 }
 
-constexpr int HB_NT = 256;
-__global__ void __launch_bounds__(HB_NT, 3) k_hbup_cascade(HbCascadeParams p, SrcView src, DstView dst)
+#ifndef R8BGPU_HB_NT
+#define R8BGPU_HB_NT 256
+#endif
+#ifndef R8BGPU_HB_MINB
+#define R8BGPU_HB_MINB 3
+#endif
+__global__ void __launch_bounds__(HB_NT, R8BGPU_HB_MINB) k_hbup_cascade(HbCascadeParams p, SrcView src, DstView dst)
 {
     extern __shared__ double hsm[];
     const int tid = threadIdx.x;
