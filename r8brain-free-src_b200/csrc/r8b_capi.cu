@@ -782,17 +782,19 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.lo_off[k] = (p.lo_off[k + 1] + 1) / 2 + T - 1;
                 p.hi_off[k] = (p.hi_off[k + 1] >= 1 ? (p.hi_off[k + 1] - 1) / 2 : -1) + T + 1;
             }
+            p.fuse_last2 = (cl >= 2 && hb_last2_supported(p.ntaps[cl - 2], p.ntaps[cl - 1]) && !getenv("R8BGPU_HB_NO_LAST2")) ? 1 : 0;
+            const int nbuf = p.fuse_last2 ? cl - 1 : cl; // streams 0 .. nbuf-1 live in shared memory
             int halo = 0;
-            for (int k = 0; k < cl; k++) halo += p.lo_off[k] + p.hi_off[k] + 8;
+            for (int k = 0; k < nbuf; k++) halo += p.lo_off[k] + p.hi_off[k] + 8;
             int budget = 14336; // doubles of shared memory per CTA (2 CTAs per SM; measured best); buffers carry a 5/4 skew
             if (const char* e = getenv("R8BGPU_HB_SMEM_DOUBLES")) budget = atoi(e);
-            int w = (((budget * 4) / 5 - halo) / ((1 << cl) - 1)) & ~31;
+            int w = (((budget * 4) / 5 - halo) / ((1 << nbuf) - 1)) & ~31;
             if (w > 1024) w = 1024;
             if (w < 32) w = 32;
             p.w = w;
             int off = 0;
-            for (int k = 0; k < cl; k++) {
-                p.boff[k] = off + p.lo_off[k] * 0; // buffer k starts at its own lo bound
+            for (int k = 0; k < nbuf; k++) {
+                p.boff[k] = off; // buffer k starts at its own lo bound
                 off += (((w << k) + p.lo_off[k] + p.hi_off[k] + 8) * 5 + 3) / 4 + 2; // + slack: threads work in quads; 5/4 skew
                 off = (off + 1) & ~1;
             }
@@ -1159,7 +1161,7 @@ static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, co
         if (!in_plain) {
             launch_to_f64(in.format, rin, in.interleaved != 0, in.interleaved ? (size_t) nch : in_cap, din, in_cap, l,
                           nch, in.scale, b->s_comp);
-            b->launches++;
+            if (l > 0) b->launches++;
         }
         if (P.passthrough) {
             if (l > 0) cudaMemcpy2DAsync(dout, o_cap * sizeof(double), din, in_cap * sizeof(double),
@@ -1170,7 +1172,7 @@ static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, co
         if (!out_plain) {
             launch_from_f64(out.format, rout, out.interleaved != 0, out.interleaved ? (size_t) nch : o_cap, dout, o_cap,
                             n, nch, out.scale, b->s_comp);
-            b->launches++;
+            if (n > 0) b->launches++;
         }
         cudaEventRecord(b->ev_k[(size_t) gi], b->s_comp);
         cudaStreamWaitEvent(b->s_d2h, b->ev_k[(size_t) gi], 0);
@@ -1267,7 +1269,7 @@ int r8bgpu_batch_process_fmt(r8bgpu_batch* b, const r8bgpu_buffer* d_in, int l, 
     if (!in_plain) {
         launch_to_f64(d_in->format, d_in->data, d_in->interleaved != 0, d_in->stride, b->st_in, in_cap, l, b->n_ch,
                       d_in->scale, st);
-        b->launches++;
+        if (l > 0) b->launches++;
         src = b->st_in;
         src_stride = in_cap;
     }
@@ -1282,7 +1284,7 @@ int r8bgpu_batch_process_fmt(r8bgpu_batch* b, const r8bgpu_buffer* d_in, int l, 
     if (!out_plain) {
         launch_from_f64(d_out->format, d_out->data, d_out->interleaved != 0, d_out->stride, b->st_out, o_cap, n, b->n_ch,
                         d_out->scale, st);
-        b->launches++;
+        if (n > 0) b->launches++;
     }
     if (!cuda_ok(cudaGetLastError(), "batch_process_fmt: kernel launch")) return -1;
     return n;

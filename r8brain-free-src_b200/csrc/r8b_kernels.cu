@@ -18,6 +18,7 @@
 
 #include "r8b_fft.cuh"
 #include "r8b_interp.cuh"
+#include "r8b_hbfuse.cuh"
 
 namespace r8bgpu {
 
@@ -480,11 +481,71 @@ __device__ __forceinline__ void hb_stage(const double* __restrict__ in, long lon
     }
 }
 
+// The last two stages of the cascade in one pass (r8b_hbfuse.cuh): reads s_{c-2} from shared memory, writes s_c to
+// global memory; s_{c-1} exists only in registers.  L, H: the tile's range of s_c (L >= 0, multiple of 8 apart).
+template <int T1, int T2>
+__device__ __forceinline__ void hb_stage_last2(const double* __restrict__ in, long long in_lo, const double* __restrict__ f1,
+                                               const double* __restrict__ f2, long long L, long long H,
+                                               const HbCascadeParams& p, const DstView& dst, int ch, int tid)
+{
+    using G = HbFuseGeom<T1, T2>;
+    const long long n_lo = L >> 1;                 // first s_{c-1} position of the tile (even: L is a multiple of 4)
+    const int n_items = (int) ((H - L) >> 3);      // 8 outputs each
+    const int base = (int) ((n_lo >> 1) + G::UB - in_lo); // buffer-local index of item 0's first u sample
+    const bool neg = n_lo - T2 + 1 < 0;            // only the very first tile of a stream
+    double fr[T1], gr[T2];
+#pragma unroll
+    for (int j = 0; j < T1; j++) fr[j] = f1[j];
+#pragma unroll
+    for (int j = 0; j < T2; j++) gr[j] = f2[j];
+    const int NL = (int) (H - L);
+    int jl = 0, jh = NL; // clip to the call's output range, in tile-local coordinates
+    if (p.e0 > L) jl = (int) (p.e0 - L);
+    if (p.e1 < H) jh = (int) (p.e1 - L);
+    double* const obase = (dst.mask == -1) ? dst.ptr + (long long) ch * dst.stride + (L - dst.base) : nullptr;
+    const bool vec_ok = obase != nullptr && ((reinterpret_cast<unsigned long long>(obase) & 15) == 0);
+    for (int q = tid; q < n_items; q += HB_NT) {
+        const int o0 = base + 2 * q;
+        double y8[8];
+        hb_fused_item<T1, T2>(fr, gr, [&](int s) { return in[hb_pad(o0 + s)]; }, n_lo + 4LL * q, neg, y8);
+        const int j0 = 8 * q;
+        if (vec_ok && j0 >= jl && j0 + 8 <= jh) {
+#pragma unroll
+            for (int m = 0; m < 4; m++)
+                *reinterpret_cast<double2*>(obase + j0 + 2 * m) = make_double2(y8[2 * m], y8[2 * m + 1]);
+        } else if (obase != nullptr) {
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                if (j0 + m >= jl && j0 + m < jh) obase[j0 + m] = y8[m];
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                if (j0 + m >= jl && j0 + m < jh) dst_write(dst, ch, L + j0 + m, y8[m]);
+        }
+    }
+}
+
+// (T1, T2) pairs the fused last-two-stages pass is instantiated for.
+bool hb_last2_supported(int t1, int t2) { return t1 >= 1 && t1 <= 6 && t2 >= 1 && t2 <= 4; }
+
+template <int T1>
+__device__ __forceinline__ void hb_last2_dispatch(int t2, const double* in, long long in_lo, const double* f1, const double* f2,
+                                                  long long L, long long H, const HbCascadeParams& p, const DstView& dst,
+                                                  int ch, int tid)
+{
+    switch (t2) {
+    case 1: hb_stage_last2<T1, 1>(in, in_lo, f1, f2, L, H, p, dst, ch, tid); break;
+    case 2: hb_stage_last2<T1, 2>(in, in_lo, f1, f2, L, H, p, dst, ch, tid); break;
+    case 3: hb_stage_last2<T1, 3>(in, in_lo, f1, f2, L, H, p, dst, ch, tid); break;
+    default: hb_stage_last2<T1, 4>(in, in_lo, f1, f2, L, H, p, dst, ch, tid); break;
+    }
+}
+
 #ifndef R8BGPU_HB_NT
 #define R8BGPU_HB_NT 256
 #endif
 #ifndef R8BGPU_HB_MINB
-#define R8BGPU_HB_MINB 3
+#define R8BGPU_HB_MINB 2 // two CTAs per SM is what the shared-memory tile allows; 123 registers, no spills (3: 80 + spills, slower)
 #endif
 __global__ void __launch_bounds__(HB_NT, R8BGPU_HB_MINB) k_hbup_cascade(HbCascadeParams p, SrcView src, DstView dst)
 {
@@ -505,6 +566,20 @@ __global__ void __launch_bounds__(HB_NT, R8BGPU_HB_MINB) k_hbup_cascade(HbCascad
     for (int k = 0; k < c; k++) {
         const double* __restrict__ in = hsm + p.boff[k];
         const long long in_lo = (A << k) - p.lo_off[k];
+        if (p.fuse_last2 && k + 2 == c) { // stages c-2 and c-1 in one pass; s_{c-1} never reaches shared memory
+            const long long L2 = A << c, H2 = (A + p.w) << c;
+            const double* f1 = p.taps[k];
+            const double* f2 = p.taps[k + 1];
+            switch (p.ntaps[k]) {
+            case 1: hb_last2_dispatch<1>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
+            case 2: hb_last2_dispatch<2>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
+            case 3: hb_last2_dispatch<3>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
+            case 4: hb_last2_dispatch<4>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
+            case 5: hb_last2_dispatch<5>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
+            default: hb_last2_dispatch<6>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
+            }
+            break;
+        }
         const bool last = (k + 1 == c);
         const long long L = last ? (A << c) : ((A << (k + 1)) - p.lo_off[k + 1]);
         const long long H = last ? ((A + p.w) << c) : (((A + p.w) << (k + 1)) + p.hi_off[k + 1]);

@@ -75,7 +75,9 @@ struct HbCascadeParams {
     int n_tiles;
     int lo_off[7], hi_off[7]; // stage-k stream range a tile needs: [2^k*A - lo_off[k], 2^k*(A+w) + hi_off[k])
     int boff[7];           // offsets (doubles) of the per-stage buffers in dynamic shared memory
+    int fuse_last2;        // stages c-2 and c-1 run as one pass (no buffer for stream c-1)
 };
+bool hb_last2_supported(int t1, int t2);
 void launch_hbup_cascade(const HbCascadeParams& p, int smem_bytes, const SrcView& src, const DstView& dst,
                          int n_ch, cudaStream_t st);
 
