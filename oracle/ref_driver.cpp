@@ -75,6 +75,33 @@ R8BREF_API void r8bref_oneshot(void* h, const double* in, int inlen, double* out
     ((CDSPResampler*) h)->oneshot(in, inlen, out, outlen);
 }
 
+// oneshot<Tin,Tout> with the reference's own sample conversions (CDSPResampler.h:592-651): pins the cast
+// semantics that the device-side sample formats restate.  Type codes follow r8bgpu_sample_format:
+// 0 double, 1 float, 2 int16, 4 int32.  Returns 0, or -1 for an unknown type pair.
+template <typename Tin>
+static int oneshot_out(CDSPResampler* rs, const Tin* in, int inlen, int tout, void* out, int outlen)
+{
+    switch (tout) {
+    case 0: rs->oneshot(in, inlen, (double*) out, outlen); return 0;
+    case 1: rs->oneshot(in, inlen, (float*) out, outlen); return 0;
+    case 2: rs->oneshot(in, inlen, (short*) out, outlen); return 0;
+    case 4: rs->oneshot(in, inlen, (int*) out, outlen); return 0;
+    default: return -1;
+    }
+}
+
+R8BREF_API int r8bref_oneshot_typed(void* h, int tin, const void* in, int inlen, int tout, void* out, int outlen)
+{
+    CDSPResampler* rs = (CDSPResampler*) h;
+    switch (tin) {
+    case 0: return oneshot_out(rs, (const double*) in, inlen, tout, out, outlen);
+    case 1: return oneshot_out(rs, (const float*) in, inlen, tout, out, outlen);
+    case 2: return oneshot_out(rs, (const short*) in, inlen, tout, out, outlen);
+    case 4: return oneshot_out(rs, (const int*) in, inlen, tout, out, outlen);
+    default: return -1;
+    }
+}
+
 // ---------------------------------------------------------------- single stages
 
 struct RefStage {

@@ -66,6 +66,9 @@ class RefOracle:
         L.r8bref_latency_frac.argtypes = [C.c_void_p]
         L.r8bref_process.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int]
         L.r8bref_oneshot.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int]
+        if hasattr(L, "r8bref_oneshot_typed"):
+            L.r8bref_oneshot_typed.restype = C.c_int
+            L.r8bref_oneshot_typed.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.r8bref_stage_blockconv.restype = C.c_void_p
         L.r8bref_stage_blockconv.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
         L.r8bref_stage_frac.restype = C.c_void_p
@@ -126,6 +129,16 @@ class RefOracle:
                 x = np.ascontiguousarray(x, dtype=np.float64)
                 out = np.empty(oplen)
                 L.r8bref_oneshot(self.h, x.ctypes.data, len(x), out.ctypes.data, oplen)
+                return out
+
+            def oneshot_typed(self, x, oplen, out_dtype):
+                """The reference's oneshot<Tin,Tout>() with ITS OWN sample conversions."""
+                codes = {"float64": 0, "float32": 1, "int16": 2, "int32": 4}
+                x = np.ascontiguousarray(x)
+                out = np.empty(oplen, dtype=out_dtype)
+                rc = L.r8bref_oneshot_typed(self.h, codes[x.dtype.name], x.ctypes.data, len(x),
+                                            codes[np.dtype(out_dtype).name], out.ctypes.data, oplen)
+                assert rc == 0
                 return out
 
         class Stage:

@@ -145,3 +145,27 @@ def test_reference_drums_kat_full_file():
         diff = (q - d[:, ch])[EDGE:-EDGE]
         assert np.max(np.abs(diff)) <= 1
         assert 20 * np.log10(np.sqrt(np.mean((diff / 2 ** 23) ** 2))) <= -141.0
+
+
+# ---- sample-format semantics: what "(double) ip[i]" / "(Tout) op[i]" do in the reference ----------
+@pytest.mark.parametrize("in_dtype,out_dtype", [
+    (np.int16, np.float32), (np.int16, np.int16), (np.int16, np.int32), (np.float32, np.int16), (np.int32, np.float32),
+])
+def test_reference_oneshot_casts_are_the_c_cast_model(ref, in_dtype, out_dtype):
+    """The GPU sample-format tests compare against 'fp64 path + C conversion in numpy' (tests/test_gpu_formats.py::c_cast).
+    This pins that model to the reference itself: oneshot<Tin,Tout>() == c_cast(oneshot<double,double>(widened input))."""
+    rng = np.random.default_rng(3)
+    if np.issubdtype(in_dtype, np.integer):
+        x = rng.integers(-12000, 12000, size=5000).astype(in_dtype)
+    else:
+        x = (rng.uniform(-12000, 12000, size=5000)).astype(in_dtype)
+    oplen = 10000
+    a = ref.Resampler(44100.0, 96000.0, 1024, 2.0, 180.15).oneshot_typed(x, oplen, out_dtype)
+    y = ref.Resampler(44100.0, 96000.0, 1024, 2.0, 180.15).oneshot(x.astype(np.float64), oplen)
+    if out_dtype == np.float32:
+        want = y.astype(np.float32)                       # round to nearest
+    else:
+        info = np.iinfo(out_dtype)
+        assert y.min() > info.min and y.max() < info.max  # in range: the reference's cast is defined
+        want = np.trunc(y).astype(out_dtype)              # toward zero
+    assert np.array_equal(a, want)
