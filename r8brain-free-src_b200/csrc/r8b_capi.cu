@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "r8b_fft.cuh"
+#include "r8b_hosttab.h"
 #include "r8b_kernels.h"
 #include "r8b_plan.h"
 
@@ -62,69 +63,6 @@ struct DeviceGuard {
         if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
     }
 };
-
-// Spectrum of the polyphase-packed filter in FFT slot order (see k_blockconv).
-template <int M>
-void fill_slot_order(const std::vector<double2>& nat, std::vector<double2>& out)
-{
-    out.resize((size_t) M);
-    for (int k = 0; k < M; k++) out[(size_t) slot_of<M>(k)] = nat[(size_t) k];
-}
-
-void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec_slots,
-                    std::vector<double2>& tw, double* nyq_gain)
-{
-    const int M = 1 << fft_log2;
-    const int L = s.lp.half_len, U = (s.up > 2) ? 1 : s.up; // up = 3 runs on the zero-stuffed stream
-    const long double two_pi = 6.283185307179586476925286766559005768L;
-    std::vector<long double> cs((size_t) M), sn((size_t) M);
-    for (int k = 0; k < M; k++) {
-        // exact octant symmetries are not needed at long-double accuracy
-        const long double a = two_pi * (long double) k / (long double) M;
-        cs[(size_t) k] = cosl(a);
-        sn[(size_t) k] = sinl(a);
-    }
-    tw.resize((size_t) M);
-    for (int k = 0; k < M; k++) tw[(size_t) k] = make_double2((double) cs[(size_t) k], (double) -sn[(size_t) k]);
-
-    // g[j] = h[U*j] + i*h[U*j+1] (U==2) or h[j] (U==1), j in [-lg, lg]
-    const int lg = (L + U - 1) / U;
-    const double* h = s.lp.taps.data() + L; // h[-L..L]
-    auto tap = [&](long long idx) -> long double {
-        return (idx < -L || idx > L) ? 0.0L : (long double) h[idx];
-    };
-    const long double scale = 1.0L / ((long double) M * (U == 2 ? 2.0L : 1.0L));
-    std::vector<double2> nat((size_t) M);
-    for (int k = 0; k < M; k++) {
-        long double re = 0.0L, im = 0.0L;
-        for (int j = -lg; j <= lg; j++) {
-            const long double gr = tap((long long) U * j);
-            const long double gi = (U == 2) ? tap((long long) U * j + 1) : 0.0L;
-            if (gr == 0.0L && gi == 0.0L) continue;
-            const int idx = (int) ((((long long) j * k) % M + M) % M);
-            const long double c = cs[(size_t) idx], sv = -sn[(size_t) idx]; // exp(-i*2pi*j*k/M)
-            re += gr * c - gi * sv;
-            im += gr * sv + gi * c;
-        }
-        nat[(size_t) k] = make_double2((double) (re * scale), (double) (im * scale));
-    }
-    if (s.block_exact) {
-        // Power-of-two decimation in the reference = inverse transform of only the lowest 1/D of
-        // the block spectrum (CDSPBlockConvolver.h:329-344).  Same thing here: the bins that the
-        // shorter inverse FFT never sees are zeroed and the full-length inverse is sampled every
-        // D-th point.  (The folded Nyquist term kb[z]*p[z]-kb[z+1]*p[z+1] is the product of two
-        // stop-band values, far below one ulp of the output, and is dropped.)
-        const int keep = M / (2 * s.down);
-        if (nyq_gain) *nyq_gain = nat[(size_t) keep].x;
-        for (int k = keep; k <= M - keep; k++) nat[(size_t) k] = make_double2(0.0, 0.0);
-    }
-    switch (fft_log2) {
-    case 10: fill_slot_order<1024>(nat, spec_slots); break;
-    case 11: fill_slot_order<2048>(nat, spec_slots); break;
-    case 13: fill_slot_order<8192>(nat, spec_slots); break;
-    default: fill_slot_order<4096>(nat, spec_slots); break;
-    }
-}
 
 int choose_fft_log2(int lg, int max_log2)
 {
@@ -175,6 +113,10 @@ struct StageDev {
     cudaEvent_t ft_ev[2] = {nullptr, nullptr};
     int ft_cur = 0;
     int casc_len = 0; // >= 2 on the first stage of a run of HBUP stages executed by k_hbup_cascade
+    // v2 fused kernel (r8b_fused2.cu): [q][r] twiddle tables for the bulk copy; on the BLOCKCONV stage
+    double2* tw_tab = nullptr;
+    bool f2_ok = false;
+    FusedGeom fgeom;
 };
 
 } // namespace
@@ -212,6 +154,8 @@ struct r8bgpu_batch {
     int host_groups = 1;
     std::vector<cudaEvent_t> ev_h2d, ev_k;
     unsigned long long* prof = nullptr; // R8BGPU_PROFILE: phase cycle counters of the fused kernel
+    int n_sm = 0;     // SMs of the device (grid of the persistent v2 fused kernel)
+    int f2_flags = 3; // v2 fused kernel: bit 0 ping-pong token, bit 1 bulk-copied input tiles
     unsigned long long prof_ctas = 0;
 
     ~r8bgpu_batch()
@@ -236,6 +180,7 @@ struct r8bgpu_batch {
         for (auto& d : dev) {
             cudaFree(d.spec);
             cudaFree(d.tw);
+            cudaFree(d.tw_tab);
             cudaFree(d.bank);
             cudaFree(d.ring);
             cudaFree(d.phase_off);
@@ -425,6 +370,8 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
     b->n_ch = n_channels;
     b->device = device;
     b->sched.init(b->plan);
+    if (!cuda_ok(cudaDeviceGetAttribute(&b->n_sm, cudaDevAttrMultiProcessorCount, device), "batch_create: SM count")) return nullptr;
+    if (const char* e = getenv("R8BGPU_F2_FLAGS")) b->f2_flags = atoi(e);
     const auto& st = b->plan->stages;
     b->dev.resize(st.size());
     for (size_t i = 0; i < st.size(); i++) {
@@ -432,31 +379,16 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
         StageDev& d = b->dev[i];
         const long long emit_in = (i == 0) ? 0 : st[i - 1].max_out_len;
         // Fusable pair: [BlockConv 2/1 with a kernel that fits M=4096 tiles] -> [FracInterp].
-        if (s.kind == ST_BLOCKCONV && s.up == 2 && s.down == 1 && !s.block_exact && i + 1 < st.size() &&
-            (st[i + 1].kind == ST_FRAC_WHOLE || st[i + 1].kind == ST_FRAC_POLY) && !getenv("R8BGPU_NO_FUSION")) {
-            const StageDesc& f = st[i + 1];
-            const int lg = (s.lp.half_len + 1) / 2;
-            const int flen = f.bank.filter_len, fll = flen / 2 - 1;
-            int dmax = 0;
-            if (f.kind == ST_FRAC_WHOLE)
-                dmax = (int) (((long long) 9 * f.in_step + f.out_step - 1) / f.out_step) + 1; // up to 10 phases per group
-            const int yl = (fll + 2) & ~1;
-            const int yr = (dmax + flen - yl + 2 + 1) & ~1;
-            const int smax = fused_max_span(lg, yl, yr) & ~1;
-            if (smax >= 1024 && (f.kind == ST_FRAC_POLY || f.in_step < smax / 2)) {
+        if (i + 1 < st.size() && !getenv("R8BGPU_NO_FUSION")) {
+            const FusedGeom fg = fused_geometry(s, st[i + 1]);
+            if (fg.ok) {
                 d.fused_with_next = true;
                 b->dev[i + 1].fused_into_prev = true;
-                d.yl = yl;
-                d.yr = yr;
-                d.span_max = smax;
-                d.ysh = 31;
-                if (f.kind == ST_FRAC_WHOLE && (f.in_step & 1) == 0) {
-                    // lanes step by in_step doubles through the tile: make the padded stride odd
-                    int sh = 0;
-                    while (((f.in_step >> sh) & 1) == 0) sh++;
-                    d.ysh = sh < 4 ? 4 : sh;
-                    if (((f.in_step + (f.in_step >> d.ysh)) & 1) == 0) d.ysh = 31; // cannot fix; accept conflicts
-                }
+                d.fgeom = fg;
+                d.yl = fg.yl;
+                d.yr = fg.yr;
+                d.span_max = fg.span_max;
+                d.ysh = fg.ysh;
             }
         }
         if (s.kind == ST_HBUP && !d.fused_into_prev && !getenv("R8BGPU_NO_FUSION")) {
@@ -501,6 +433,11 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
             if (!cuda_ok(cudaMemcpy(d.spec, spec.data(), nb, cudaMemcpyHostToDevice), "copy spec")) return nullptr;
             if (!cuda_ok(cudaMemcpy(d.tw, tw.data(), nb, cudaMemcpyHostToDevice), "copy tw")) return nullptr;
             b->dev_bytes += 2 * nb;
+            if (d.fused_with_next) { // conflict-free [q][r] twiddle tables, one 8 KB bulk copy per CTA in the v2 kernel
+                const std::vector<double2> tt = build_tw_tab(tw);
+                if (!cuda_ok(cudaMalloc(&d.tw_tab, tt.size() * sizeof(double2)), "cudaMalloc(tw_tab)")) return nullptr;
+                if (!cuda_ok(cudaMemcpy(d.tw_tab, tt.data(), tt.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy tw_tab")) return nullptr;
+            }
         } else if (s.kind == ST_FRAC_WHOLE || s.kind == ST_FRAC_POLY) {
             const size_t nb = s.bank.table.size() * sizeof(double);
             if (!cuda_ok(cudaMalloc(&d.bank, nb), "cudaMalloc(bank)")) return nullptr;
@@ -517,62 +454,28 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 }
             }
             if (s.kind == ST_FRAC_WHOLE) {
-                // per output phase r: floor(r*InStep/OutStep) and the bank row (r*InStep) % OutStep
-                std::vector<int> off((size_t) s.out_step), row((size_t) s.out_step);
-                for (int r = 0; r < s.out_step; r++) {
-                    const long long pos = (long long) r * s.in_step;
-                    off[(size_t) r] = (int) (pos / s.out_step);
-                    row[(size_t) r] = (int) (pos % s.out_step);
-                }
-                const size_t tb = off.size() * sizeof(int);
+                // per output phase r: floor(r*InStep/OutStep) and the bank row (r*InStep) % OutStep; grouped bank for
+                // the fused kernels: IR consecutive phases share one y window
+                const GroupBank B = build_group_bank(s, choose_group_ir(s));
+                const size_t tb = B.off.size() * sizeof(int);
                 if (!cuda_ok(cudaMalloc(&d.phase_off, tb), "cudaMalloc(phase)")) return nullptr;
                 if (!cuda_ok(cudaMalloc(&d.phase_row, tb), "cudaMalloc(phase)")) return nullptr;
-                cudaMemcpy(d.phase_off, off.data(), tb, cudaMemcpyHostToDevice);
-                cudaMemcpy(d.phase_row, row.data(), tb, cudaMemcpyHostToDevice);
-                // grouped bank for the fused kernel: IR consecutive phases share one y window.  IR is 8 or
-                // 10, whichever spreads the phase groups more evenly over the kernel's 16 warps.
-                {
-                    const int flen = s.bank.filter_len;
-                    int ir = 8;
-                    {
-                        const int g8 = (s.out_step + 7) / 8, g10 = (s.out_step + 9) / 10;
-                        const int c8 = ((g8 + 15) / 16) * 8, c10 = ((g10 + 15) / 16) * 10;
-                        // measured: the 10-phase variant spills registers; where 8-phase groups can start every call
-                        // on a 64-byte output boundary (out_step % 8 == 0: cfg 2) it loses by ~4 % (2.10 vs 2.02 ms)
-                        // despite the even task split, elsewhere the split wins (cfg 3, out_step 147: 1.88 vs 1.98 ms)
-                        if (s.out_step % 8 != 0 && c10 < c8) ir = 10;
-                        if (const char* e = getenv("R8BGPU_IR")) ir = atoi(e) == 10 ? 10 : 8;
-                    }
-                    const int ng = (s.out_step + ir - 1) / ir;
-                    const int os = s.out_step;
-                    // window offset of "phase" pr >= 0 counted from cycle 0 (pr >= os continues in later cycles)
-                    auto offx = [&](int pr) { return off[(size_t) (pr % os)] + (pr / os) * s.in_step; };
-                    int dmax = 0;
-                    for (int r0 = 0; r0 < os; r0++) dmax = std::max(dmax, offx(r0 + ir - 1) - offx(r0));
-                    const int smaxp = (flen + dmax + 3) & ~3;
-                    // one entry per possible first phase r0: lets a call start its groups at e0 mod 8
-                    std::vector<double> gb((size_t) os * smaxp * ir, 0.0);
-                    std::vector<int> go((size_t) os);
-                    for (int r0 = 0; r0 < os; r0++) {
-                        go[(size_t) r0] = off[(size_t) r0];
-                        for (int r = 0; r < ir; r++) {
-                            const int pr = r0 + r;
-                            const int dr = offx(pr) - offx(r0);
-                            const double* rowp = s.bank.table.data() + (size_t) row[(size_t) (pr % os)] * flen;
-                            for (int i = 0; i < flen; i++) gb[((size_t) r0 * smaxp + dr + i) * ir + r] = rowp[i];
-                        }
-                    }
-                    d.gbank_smem_len = ng * smaxp * ir;
-                    d.ir = ir;
-                    d.gbank_len = (int) gb.size();
-                    d.smaxp = smaxp;
-                    if (!cuda_ok(cudaMalloc(&d.gbank, gb.size() * sizeof(double)), "cudaMalloc(gbank)")) return nullptr;
-                    if (!cuda_ok(cudaMalloc(&d.goff, go.size() * sizeof(int)), "cudaMalloc(goff)")) return nullptr;
-                    cudaMemcpy(d.gbank, gb.data(), gb.size() * sizeof(double), cudaMemcpyHostToDevice);
-                    cudaMemcpy(d.goff, go.data(), go.size() * sizeof(int), cudaMemcpyHostToDevice);
-                    b->dev_bytes += gb.size() * sizeof(double);
-                }
+                cudaMemcpy(d.phase_off, B.off.data(), tb, cudaMemcpyHostToDevice);
+                cudaMemcpy(d.phase_row, B.row.data(), tb, cudaMemcpyHostToDevice);
+                d.gbank_smem_len = B.n_groups * B.smaxp * B.ir;
+                d.ir = B.ir;
+                d.gbank_len = (int) B.gb.size();
+                d.smaxp = B.smaxp;
+                if (!cuda_ok(cudaMalloc(&d.gbank, B.gb.size() * sizeof(double)), "cudaMalloc(gbank)")) return nullptr;
+                if (!cuda_ok(cudaMalloc(&d.goff, B.go.size() * sizeof(int)), "cudaMalloc(goff)")) return nullptr;
+                cudaMemcpy(d.gbank, B.gb.data(), B.gb.size() * sizeof(double), cudaMemcpyHostToDevice);
+                cudaMemcpy(d.goff, B.go.data(), B.go.size() * sizeof(int), cudaMemcpyHostToDevice);
+                b->dev_bytes += B.gb.size() * sizeof(double);
                 d.bank_in_smem = (fused_smem_bytes(d.gbank_smem_len) <= 220 * 1024) ? 1 : 0;
+                // the persistent two-pipeline kernel needs the call's whole bank in shared memory
+                if (d.fused_into_prev && i > 0 && fused2_smem_bytes(d.gbank_smem_len, false) <= 227 * 1024 &&
+                    (s.out_step + d.ir - 1) / d.ir <= 192 && !getenv("R8BGPU_FUSED_V1"))
+                    b->dev[i - 1].f2_ok = true;
             }
         }
     }
@@ -643,7 +546,7 @@ int r8bgpu_batch_stage_kernel(const r8bgpu_batch* b, int stage, char* name, int 
         nm = "(fused)";
         span = 0;
     } else if (d.fused_with_next) {
-        nm = "k_up2_frac";
+        nm = d.f2_ok ? "k_up2_frac2" : "k_up2_frac";
         span = 2;
     } else if (d.casc_len >= 2) {
         nm = "k_hbup_cascade";
@@ -810,24 +713,29 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             const StageDev& fd = b->dev[i + 1];
             FusedParams p;
             memset(&p, 0, sizeof p);
-            p.mode = f.kind == ST_FRAC_WHOLE ? 0 : 1;
-            p.flen = f.bank.filter_len;
-            p.fll = p.flen / 2 - 1;
-            p.e0 = fc.e0;
-            p.e1 = fc.e1;
-            if (p.mode == 0) {
-                p.p_lo = (fc.e0 * f.in_step) / f.out_step;
-                p.p_hi = ((fc.e1 - 1) * f.in_step) / f.out_step + 1;
+            if (f.kind == ST_FRAC_WHOLE) {
+                fused_whole_fields(p, f, fc.e0, fc.e1);
             } else {
-                p.p_lo = fc.p0;
+                p.mode = 1;
+                p.flen = f.bank.filter_len;
+                p.fll = p.flen / 2 - 1;
+                p.e0 = fc.e0;
+                p.e1 = fc.e1;
+                p.p_lo = fc.p0 & ~1LL; // even (positions are >= 0)
                 p.p_hi = fc.p_last + 1;
+                p.in_step = f.in_step;
+                p.out_step = f.out_step;
             }
-            p.p_lo &= ~1LL; // even (positions are >= 0)
-            const long long range = p.p_hi - p.p_lo;
-            long long nt = (range + d.span_max - 1) / d.span_max;
-            if (nt > 1 && (nt & 1)) nt++;
-            p.n_tiles = (int) nt;
-            p.span = (int) (((range + nt - 1) / nt + 1) & ~1LL);
+            const bool v2 = d.f2_ok && p.mode == 0;
+            if (v2) {
+                fused2_tiles(p, d.fgeom, i == 0 ? (int) (c.n0 & 1) : -1);
+            } else {
+                const long long range = p.p_hi - p.p_lo;
+                long long nt = (range + d.span_max - 1) / d.span_max;
+                if (nt > 1 && (nt & 1)) nt++;
+                p.n_tiles = (int) nt;
+                p.span = (int) (((range + nt - 1) / nt + 1) & ~1LL);
+            }
             p.yl = d.yl;
             p.lg = d.lg;
             p.ysh = d.ysh;
@@ -842,16 +750,12 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.goff = fd.goff;
             p.ir = fd.ir;
             p.gbank_smem_len = fd.gbank_smem_len;
-            p.wrap = (p.mode == 0 && f.out_step % 8 == 0 && !getenv("R8BGPU_NO_ALIGN")) ? 1 : 0;
-            p.delta = p.wrap ? (int) (fc.e0 & 7) : 0;
             {
                 // store staging area behind the bank, if shared memory allows (whole stepping, 8-phase groups)
                 const int used = fused_fixed_doubles() + (p.bank_in_smem ? ((p.gbank_smem_len + 1) & ~1) : 0);
                 p.stage_off = (p.mode == 0 && p.ir == 8 && !getenv("R8BGPU_NO_STAGE") &&
                                (used + fused_stage_doubles()) * 8 <= 224 * 1024) ? used : 0;
             }
-            p.in_step = f.in_step;
-            p.out_step = f.out_step;
             p.phase_off = fd.phase_off;
             p.phase_row = fd.phase_row;
             p.fracs = f.bank.fracs;
@@ -894,9 +798,21 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 cudaMemset(b->prof, 0, 10 * sizeof(unsigned long long));
             }
             p.prof = b->prof;
+#ifdef R8BGPU_EXPERIMENTS
             if (const char* e = getenv("R8BGPU_DEBUG")) p.debug = atoi(e);
+#endif
             if (b->prof) b->prof_ctas += (unsigned long long) ((p.n_tiles + 1) / 2) * nch;
-            launch_up2_frac(p, src, dst, nch, st);
+            if (v2) {
+                p.n_ch = nch;
+                p.flags = b->f2_flags;
+                p.tw_tab = d.tw_tab;
+                p.stage_off = (p.ir == 8 && fused2_smem_bytes(p.gbank_smem_len, true) <= 227 * 1024 && !getenv("R8BGPU_NO_STAGE"))
+                                  ? fused2_stage_off(p.gbank_smem_len) : 0;
+                p.glog = fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
+                launch_up2_frac2(p, src, dst, b->n_sm, st);
+            } else {
+                launch_up2_frac(p, src, dst, nch, st);
+            }
             b->launches++;
         } else
         switch (s.kind) {

@@ -18,13 +18,25 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cmath>
+
+// R8B_HD: the butterflies are plain arithmetic; host builds of them back the CPU emulation of the fused
+// kernel that tests/ runs without a GPU (tests/cpp/fused2_emul.cu).
+#define R8B_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define R8B_LDG(p) __ldg(p)
+#else
+#define R8B_LDG(p) (*(p))
+using std::fma;
+#endif
+
 namespace r8bgpu {
 
 __host__ __device__ __forceinline__ constexpr int fft_pad(int i) { return i + (i >> 4); }
 __host__ __device__ __forceinline__ constexpr int fft_padded_len(int m) { return m + (m >> 4); }
 
 template <int DIR>
-__device__ __forceinline__ double2 cmul(double2 a, double2 w)
+R8B_HD double2 cmul(double2 a, double2 w)
 {
     // DIR > 0: a*w ; DIR < 0: a*conj(w)
     if (DIR > 0) return make_double2(fma(a.x, w.x, -a.y * w.y), fma(a.x, w.y, a.y * w.x));
@@ -33,7 +45,7 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 w)
 
 // a * W_R^K, W_R = exp(-DIR * 2*pi*i / R), 0 <= K < R/2 (compile-time).
 template <int R, int K, int DIR>
-__device__ __forceinline__ double2 mul_root(double2 a)
+R8B_HD double2 mul_root(double2 a)
 {
     constexpr double kH = 0.70710678118654752440; // sqrt(1/2)
     if constexpr (K == 0) {
@@ -60,7 +72,7 @@ __device__ __forceinline__ double2 mul_root(double2 a)
 
 template <int N, int DIR, int I>
 struct BflyStage {
-    static __device__ __forceinline__ void run(double2* v)
+    static R8B_HD void run(double2* v)
     {
         const double2 a = v[I], b = v[I + N / 2];
         v[I] = make_double2(a.x + b.x, a.y + b.y);
@@ -72,7 +84,7 @@ struct BflyStage {
 // Radix-2 DIF network on N register values: input natural order, output k at v[bitrev(k)].
 template <int N, int DIR>
 struct Network {
-    static __device__ __forceinline__ void run(double2* v)
+    static R8B_HD void run(double2* v)
     {
         BflyStage<N, DIR, 0>::run(v);
         if constexpr (N > 2) {
@@ -91,6 +103,7 @@ __host__ __device__ __forceinline__ constexpr int bitrev(int q)
     return r;
 }
 
+#ifdef __CUDACC__ // block-wide passes: device code only
 // One DIF pass over all blocks of length NCUR (M/R butterflies), data in padded smem.
 template <int M, int NCUR, int R, int NT>
 __device__ __forceinline__ void fft_pass_forward(double2* __restrict__ s,
@@ -179,6 +192,8 @@ __device__ __forceinline__ void fft_inverse(double2* s, const double2* tw, int t
         __syncthreads();
     }
 }
+
+#endif // __CUDACC__
 
 // Frequency index k (0..M-1) <-> storage slot after fft_forward.
 //   k = q1 + R1*(q2 + 16*q3)  ->  slot = q1*256 + q2*16 + q3

@@ -21,45 +21,17 @@
 
 #include <climits>
 
-#include "r8b_fft.cuh"
+#include "r8b_fused_common.cuh"
 #include "r8b_interp.cuh"
 
 namespace r8bgpu {
 
 namespace {
 
-__device__ __forceinline__ double src_read_f(const SrcView& v, int ch, long long n)
-{
-    if (n >= v.avail) return 0.0;
-    if (n >= v.cur_base) return __ldg(v.cur + (long long) ch * v.cur_stride + (n - v.cur_base));
-    return __ldg(v.ring + (long long) ch * v.ring_stride + (n & v.ring_mask));
-}
-
-__device__ __forceinline__ void dst_write_f(const DstView& v, int ch, long long idx, double x)
-{
-    v.ptr[(long long) ch * v.stride + ((idx - v.base) & v.mask)] = x;
-}
-
-constexpr int FM = 4096;            // FFT length of the fused kernel
 constexpr int FNT = 512;            // threads per CTA
-constexpr int FPL = fft_padded_len(FM);
 // interpolation register tile: IR output phases per lane (8 or 10, chosen per plan so that the
 // number of phase groups divides evenly over the 16 warps) x IQ stepping cycles per lane
 constexpr int IQ = 3;               // ... x stepping cycles per lane
-
-__device__ __forceinline__ int ylay(int i, int ysh) { return i + (i >> ysh); }
-
-// Twiddles from shared memory, laid out [q][r] so that the 16 consecutive lanes of a half-warp read 16
-// consecutive entries (the natural [r*q] indexing is an up-to-16-way bank conflict for even q):
-//   tw2t[q*16 + r] = W_256^(r q)            (r, q < 16)  -- passes with NCUR = 256
-//   tw1t[q*16 + r] = W_M^(r q)              (r, q < 16)
-//   W_M^(R q), R = 16 r_hi + r_lo < 256  =  tw2t[q*16 + r_hi] * tw1t[q*16 + r_lo]   -- passes with NCUR = M
-// (one extra complex multiply, <= ~1.5 ulp, instead of walking a 64 KB table through L1/L2).
-__device__ __forceinline__ double2 tw_pair(const double2* __restrict__ tw2t, const double2* __restrict__ tw1t, int r, int q)
-{
-    const double2 c = tw2t[q * 16 + (r >> 4)], f = tw1t[q * 16 + (r & 15)];
-    return make_double2(fma(c.x, f.x, -c.y * f.y), fma(c.x, f.y, c.y * f.x));
-}
 
 // forward pass 1 fused with the gather from global memory (radix 16, NCUR = M, D = 256)
 __device__ __forceinline__ void gather_loads(double2 (&v)[16], const SrcView& src, int ch, long long wa, long long wb,
@@ -97,45 +69,6 @@ __device__ __forceinline__ void fwd_pass1_regs(double2 (&v)[16], double2* __rest
         s[fft_pad(r + q * 256)] = x;
     }
 }
-
-template <int NCUR>
-__device__ __forceinline__ void fwd_pass(double2* __restrict__ s, const double2* __restrict__ tw_g,
-                                         const double2* __restrict__ tw2_s, int g)
-{
-    constexpr int D = NCUR / 16;
-    const int blk = g / D, r = g % D;
-    const int base = blk * NCUR + r;
-    double2 v[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++) v[j] = s[fft_pad(base + j * D)];
-    Network<16, +1>::run(v);
-#pragma unroll
-    for (int q = 0; q < 16; q++) {
-        double2 x = v[bitrev<16>(q)];
-        if (D > 1 && q > 0) x = cmul<+1>(x, tw2_s[q * 16 + r]); // NCUR == 256: W_256^(r q), [q][r] layout
-        s[fft_pad(base + q * D)] = x;
-    }
-    (void) tw_g;
-}
-
-template <int NCUR>
-__device__ __forceinline__ void inv_pass(double2* __restrict__ s, const double2* __restrict__ tw2_s, int g)
-{
-    constexpr int D = NCUR / 16;
-    const int blk = g / D, r = g % D;
-    const int base = blk * NCUR + r;
-    double2 v[16];
-#pragma unroll
-    for (int q = 0; q < 16; q++) {
-        double2 x = s[fft_pad(base + q * D)];
-        if (D > 1 && q > 0) x = cmul<-1>(x, tw2_s[q * 16 + r]);
-        v[q] = x;
-    }
-    Network<16, -1>::run(v);
-#pragma unroll
-    for (int j = 0; j < 16; j++) s[fft_pad(base + j * D)] = v[bitrev<16>(j)];
-}
-
 
 // Pair-level bookkeeping for the whole-stepping interpolation, done by ONE thread at kernel start (it
 // depends only on the launch parameters, so its 64-bit divisions hide behind the input gather).  Everything the
@@ -214,7 +147,11 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
         for (int r = 0; r < IR; r++)
 #pragma unroll
             for (int q = 0; q < IQ; q++) acc[r][q] = 0.0;
-        const int s_end = (p.debug & 2) ? 0 : smaxp;
+#ifdef R8BGPU_EXPERIMENTS
+        const int s_end = (p.debug & 2) ? 0 : smaxp; // profiling experiment: skip the tap loop
+#else
+        const int s_end = smaxp;
+#endif
 #pragma unroll 4
         for (int s = 0; s < s_end; s++) { // smaxp is a multiple of 4
             double yv[IQ];
@@ -238,10 +175,12 @@ __device__ __forceinline__ void interp_whole(const FusedParams& p, const DstView
         // row-wise writes and the transposed reads are bank-conflict free.
         const bool linear = (dst.mask == -1);
         double* const obase = s_o;
-        if (p.debug & 1) {
+#ifdef R8BGPU_EXPERIMENTS
+        if (p.debug & 1) { // profiling experiment: skip the stores
             if (acc[0][0] == 1.2345e300) obase[0] = acc[1][1]; // keep the loop alive
             continue;
         }
+#endif
         if (linear && stage != nullptr && IR == 8) {
             double* const stg = stage + warp * 256;
             const int wrow = (lane ^ ((lane >> 2) & 1)) * 8, wsw = (lane >> 1) & 3;
@@ -635,10 +574,10 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
     if (tid < 256) fwd_pass1_regs(gv, bufA, twc, twf, tid);
     __syncthreads();
     R8B_TICK(0)
-    if (tid < 256) fwd_pass<256>(bufA, p.tw, tw2, tid);
+    if (tid < 256) fwd_pass<256>(bufA, tw2, tid);
     __syncthreads();
     R8B_TICK(1)
-    if (tid < 256) fwd_pass<16>(bufA, p.tw, tw2, tid);
+    if (tid < 256) fwd_pass<16>(bufA, tw2, tid);
     __syncthreads();
     R8B_TICK(2)
 
@@ -785,13 +724,7 @@ int fused_fixed_doubles() { return 2 * (2 * FPL + 256 + 256); }     // buffers +
 template <int MODE, int IRV, bool PADV, bool BANKV>
 static void launch_inst(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, int smem, cudaStream_t st)
 {
-    static bool configured[16] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 16 && !configured[dev]) {
-        cudaFuncSetAttribute(k_up2_frac<MODE, IRV, PADV, BANKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        configured[dev] = true;
-    }
+    ensure_dyn_smem<k_up2_frac<MODE, IRV, PADV, BANKV>>(224 * 1024);
     const int n_pairs = (p.n_tiles + 1) >> 1;
     k_up2_frac<MODE, IRV, PADV, BANKV><<<(unsigned) (n_pairs * n_ch), FNT, smem, st>>>(p, src, dst);
 }

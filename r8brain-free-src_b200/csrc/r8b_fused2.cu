@@ -1,0 +1,311 @@
+// r8b_fused2.cu -- v2 of the fused "2x BlockConvolver -> whole-stepping FracInterpolator" kernel
+// (CDSPResampler.h:218-333; CDSPBlockConvolver.h:252-354 + CDSPFracInterpolator.h:991-1060), the whole
+// process() chain of BASELINE configs 1/2/3 in ONE launch per call.
+//
+// v1 (r8b_fused.cu) gives an SM to one 512-thread CTA that walks a tile pair through seven block-wide
+// phases; nothing overlaps a barrier, half the CTA idles through the forward transform, and every CTA pays
+// its launch and drain (ncu: fp64 pipe 34 %, warps active 23 %).  v2 is a PERSISTENT CTA per SM made of two
+// independent 256-thread pipelines ("halves").  Each half owns one tile at a time and synchronises only
+// with itself (named barriers, bar.sync id,256); the halves are kept half a period apart by a token
+// (mbarrier ping-pong around the interpolation), so one half's transforms -- latency-bound, few warps --
+// run under the other half's interpolation -- throughput-bound.  Shared tables arrive once per CTA by
+// bulk async copy (cp.async.bulk + mbarrier): the [q][r] twiddle tables and this call's phase-group bank.
+// A tile's 4096 input samples are one contiguous 32 KB run of the caller's block: they are prefetched into
+// L2 a tile ahead (cp.async.bulk.prefetch.L2) and land in the tile buffer's upper half by one bulk copy
+// issued as soon as the half's previous tile has left the buffer; no registers are spent on prefetch.
+// Tiles at the edges of a call (history ring, not yet available input) and misaligned rows are gathered
+// with plain loads.
+//
+// Shared memory: 2 tile buffers (4096 padded double2 each) + twiddles 8 KB + bank + per-warp store staging.
+#include "r8b_kernels.h"
+
+#include <cstdint>
+
+#include "r8b_fused2_core.cuh"
+
+namespace r8bgpu {
+
+namespace {
+
+using namespace f2;
+
+constexpr int NT2 = 2 * HT;
+constexpr int STAGE_UP = fft_pad(FN);  // double2 index where a bulk-copied input tile lands (upper half of the buffer)
+
+// ---- PTX helpers: named barriers, mbarriers, bulk async copies ---------------------------------
+__device__ __forceinline__ void bar_half(int h) { asm volatile("bar.sync %0, 256;" ::"r"(h + 1) : "memory"); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Transposed stores (IR == 8, linear destination): the lane's 8 outputs of one cycle are a 64-byte row;
+// rows of neighbouring lanes are out_step samples apart, so storing straight from registers would touch 32
+// rows per instruction.  Through a 2 KB per-warp staging area the warp transposes 4x4 blocks of 16-byte
+// chunks so that 4 adjacent lanes write one whole row: 8 rows x 64 B per instruction (rows of the two
+// phase groups of a cycle are adjacent: 128 B runs).  Row R lives at prow(R)*64 B with its chunks
+// XOR-swizzled -- both the row-wise writes and the transposed reads are bank-conflict free.
+template <int GLOG>
+__device__ __forceinline__ void interp_store_staged(const FusedParams& p, const int* __restrict__ s_i, double* s_o, double* stg,
+                                                    int task, int lane, const double (&acc)[8][IQ2])
+{
+    using G = TaskGeom<8, GLOG>;
+    const int n_j = s_i[0], c_cnt = s_i[1], jshift = s_i[2];
+    const int n_groups = (p.out_step + 7) / 8;
+    const int n_gt = (n_groups + G::GL - 1) / G::GL;
+    const int gt = task % n_gt, chunk = task / n_gt;
+    const int wrow = (lane ^ ((lane >> 2) & 1)) * 8, wsw = (lane >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < IQ2; q++) {
+        const int cq = chunk * G::CYC + q * G::CL; // cycle of cycle-lane 0
+        if (cq > c_cnt) break;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            *reinterpret_cast<double2*>(stg + wrow + 2 * (i ^ wsw)) = make_double2(acc[2 * i][q], acc[2 * i + 1][q]);
+        __syncwarp();
+        const int ci = lane & 3;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int R = (lane & ~3) + t;
+            const double2 v = *reinterpret_cast<const double2*>(stg + (R ^ ((R >> 2) & 1)) * 8 + 2 * (ci ^ ((R >> 1) & 3)));
+            const int c = cq + (R & (G::CL - 1));
+            const int grp = gt * G::GL + (R >> (5 - GLOG));
+            if (c > c_cnt || grp >= n_groups) continue;
+            const int r0 = p.delta + grp * 8;
+            const int j = c * p.out_step + r0 + jshift + 2 * ci; // first of this lane's two outputs
+            double* o = s_o + j;
+            const bool in0 = (p.wrap || r0 + 2 * ci < p.out_step) && j >= 0 && j < n_j;
+            const bool in1 = (p.wrap || r0 + 2 * ci + 1 < p.out_step) && j + 1 >= 0 && j + 1 < n_j;
+            if (in0 && in1 && ((reinterpret_cast<unsigned long long>(o) & 15) == 0)) {
+                *reinterpret_cast<double2*>(o) = v;
+            } else {
+                if (in0) o[0] = v.x;
+                if (in1) o[1] = v.y;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace
+
+// flags: bit 0 = ping-pong token around the interpolation, bit 1 = bulk-copy input tiles
+template <int IRV, bool PADV, int GLOG>
+__global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ FusedParams p, const __grid_constant__ SrcView src,
+                                                      const __grid_constant__ DstView dst)
+{
+    extern __shared__ __align__(128) double2 smem[];
+    double2* const tw2 = smem + 2 * FPL;          // tw2t[q*16+r] = W_256^(r q)
+    double2* const twf = tw2 + 256;               // tw1t[q*16+r] = W_M^(r q)
+    double* const sbank = reinterpret_cast<double*>(twf + 256);
+    __shared__ __align__(8) unsigned long long mb[5]; // 0: tables, 1-2: input tile of half h, 3-4: interpolation turn of half h
+    __shared__ int s_i[2][8];
+    __shared__ double* s_o[2];
+    __shared__ int s_goff[192];
+
+    const int tid = threadIdx.x, h = tid >> 8, ht = tid & (HT - 1), lane = tid & 31, wh = ht >> 5;
+    double2* const buf = smem + h * FPL;
+    const int n_units = p.n_tiles * p.n_ch;
+    const int n_groups = (p.out_step + IRV - 1) / IRV, esz = p.smaxp * IRV;
+    const bool pingpong = (p.flags & 1) != 0, tma_in = (p.flags & 2) != 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) mbar_init(&mb[i], 1);
+        fence_mbar_init();
+    }
+    if (tid < n_groups) s_goff[tid] = __ldg(&p.goff[p.delta + tid * IRV]);
+    __syncthreads();
+    if (tid == 0) {
+        // tables: one transaction barrier, 1 + n_groups bulk copies
+        mbar_expect_tx(&mb[0], (uint32_t) (512 * sizeof(double2) + (size_t) n_groups * esz * sizeof(double)));
+        bulk_g2s(tw2, p.tw_tab, 512 * sizeof(double2), &mb[0]);
+        for (int g = 0; g < n_groups; g++)
+            bulk_g2s(sbank + g * esz, p.gbank + (long long) (p.delta + g * IRV) * esz, (uint32_t) (esz * sizeof(double)), &mb[0]);
+        mbar_arrive(&mb[3]); // half 0 interpolates first
+    }
+
+    const int stride = 2 * (int) gridDim.x;
+    int u = 2 * (int) blockIdx.x + h;
+    uint32_t par_in = 0, par_turn = 0;
+    Tile t;
+    int path = -1;
+    auto tile_src = [&](const Tile& tt) { return src.cur + (long long) tt.ch * src.cur_stride + (tt.w - src.cur_base); };
+    if (u < n_units) {
+        t = tile_of(p, u);
+        path = tile_input_path(src, t);
+        if (path == 2 && !tma_in) path = 1;
+        if (path == 2 && ht == 0) {
+            mbar_expect_tx(&mb[1 + h], FM * sizeof(double));
+            bulk_g2s(buf + STAGE_UP, tile_src(t), FM * sizeof(double), &mb[1 + h]);
+        }
+    }
+    mbar_wait(&mb[0], 0); // twiddles and bank have landed
+
+    for (; u < n_units; u += stride) {
+        // the tile after this one: its input starts moving towards L2 now
+        Tile tn = t;
+        int pathn = -1;
+        if (u + stride < n_units) {
+            tn = tile_of(p, u + stride);
+            pathn = tile_input_path(src, tn);
+            if (pathn == 2 && !tma_in) pathn = 1;
+            if (pathn != 0 && ht == 0) bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<unsigned long long>(tile_src(tn)) & ~15ull),
+                                                        FM * sizeof(double));
+        }
+        // A. input -> registers -> radix-8 pass into the lower half of the buffer
+        {
+            double2 v[8];
+            if (path == 2) {
+                mbar_wait(&mb[1 + h], par_in);
+                par_in ^= 1;
+                const double2* st = buf + STAGE_UP;
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = st[ht + 256 * j];
+            } else {
+                gather_tile(v, src, t, path, ht);
+            }
+            fwd_pass1_r8(v, buf, tw2, twf, ht);
+        }
+        if (ht == HT - 1) interp_prepare(p, dst, t, s_i[h], &s_o[h]);
+        bar_half(h);
+        // B. the two radix-16 passes act on 256-point blocks owned by one half-warp each
+        if (ht < FN / 16) {
+            fwd_pass<256>(buf, tw2, ht);
+            __syncwarp();
+            fwd_pass<16>(buf, tw2, ht);
+        }
+        bar_half(h);
+        // C. split + multiply by the filter spectrum, in place (all loads before the first store)
+        {
+            double2 z1[4], z2[4], ze = make_double2(0.0, 0.0);
+            c_load(buf, ht, z1, z2);
+            if (ht == 0) ze = buf[fft_pad(slot_of<FN>(FN / 2))];
+            bar_half(h);
+#pragma unroll
+            for (int i = 0; i < 4; i++) c_pair(p, buf, c_freq(ht, i), z1[i], z2[i]);
+            if (ht == 0) c_pair(p, buf, FN / 2, ze, ze);
+        }
+        bar_half(h);
+        // D. inverse transform
+        inv_pass<16>(buf, tw2, ht);
+        __syncwarp();
+        inv_pass<256>(buf, tw2, ht);
+        bar_half(h);
+        {
+            double2 v[16];
+            inv3_load(buf, tw2, twf, ht, v);
+            bar_half(h);
+            y_store<PADV>(buf, v, ht, t.w, p.ysh);
+        }
+        bar_half(h);
+        // E. interpolation out of shared memory
+        if (pingpong) {
+            mbar_wait(&mb[3 + h], par_turn);
+            par_turn ^= 1;
+        }
+        {
+            const double* yb = reinterpret_cast<const double*>(buf);
+            const int* si = s_i[h];
+            if (si[0] > 0) {
+                const int n_tasks = TaskGeom<IRV, GLOG>::n_tasks(p, si[1]);
+                double* const stg = p.stage_off > 0 ? reinterpret_cast<double*>(smem) + p.stage_off + (tid >> 5) * 256 : nullptr;
+                for (int task = wh; task < n_tasks; task += HT / 32) {
+                    TaskGeom<IRV, GLOG> g;
+                    g.set(p, s_goff, task, lane);
+                    int yo[IQ2];
+                    interp_windows<IRV, GLOG>(p, g, si, yo);
+                    double acc[IRV][IQ2];
+                    interp_acc<IRV, PADV>(yb, sbank + g.grp * esz, yo, p.smaxp, p.ysh, acc);
+                    if (IRV == 8 && dst.mask == -1 && stg != nullptr) {
+                        if constexpr (IRV == 8) interp_store_staged<GLOG>(p, si, s_o[h], stg, task, lane, acc);
+                    } else {
+                        interp_store_direct<IRV, GLOG>(p, dst, t.ch, g, si, s_o[h], acc);
+                    }
+                }
+            }
+        }
+        bar_half(h); // the buffer is free again
+        if (ht == 0) {
+            if (pingpong) mbar_arrive(&mb[4 - h]);
+            if (pathn == 2) {
+                fence_proxy_async(); // generic-proxy reads of the buffer are ordered before the async-proxy write
+                mbar_expect_tx(&mb[1 + h], FM * sizeof(double));
+                bulk_g2s(buf + STAGE_UP, tile_src(tn), FM * sizeof(double), &mb[1 + h]);
+            }
+        }
+        t = tn;
+        path = pathn;
+    }
+}
+
+int fused2_smem_bytes(int bank_doubles, bool staged)
+{
+    return 2 * FPL * (int) sizeof(double2) + 512 * (int) sizeof(double2) + ((bank_doubles + 1) & ~1) * (int) sizeof(double) +
+           (staged ? (NT2 / 32) * 256 * (int) sizeof(double) : 0);
+}
+int fused2_stage_off(int bank_doubles) { return 2 * (2 * FPL + 512) + ((bank_doubles + 1) & ~1); }
+
+template <int IRV, bool PADV, int GLOG>
+static void launch_inst2(const FusedParams& p, const SrcView& src, const DstView& dst, int grid, int smem, cudaStream_t st)
+{
+    ensure_dyn_smem<k_up2_frac2<IRV, PADV, GLOG>>(227 * 1024);
+    k_up2_frac2<IRV, PADV, GLOG><<<(unsigned) grid, NT2, smem, st>>>(p, src, dst);
+}
+
+// p.n_ch, p.n_tiles, p.span ... describe the call; n_sm = SMs of the device (persistent grid).
+void launch_up2_frac2(const FusedParams& p, const SrcView& src, const DstView& dst, int n_sm, cudaStream_t st)
+{
+    const int n_units = p.n_tiles * p.n_ch;
+    if (n_units <= 0) return;
+    int grid = (n_units + 1) / 2;
+    if (grid > n_sm) grid = n_sm;
+    const int smem = fused2_smem_bytes(p.gbank_smem_len, p.stage_off > 0);
+    const bool pad = p.ysh != 31;
+#define R8B_F2_CASE(IRV, GL)                                                              \
+    if (pad) launch_inst2<IRV, true, GL>(p, src, dst, grid, smem, st);                    \
+    else launch_inst2<IRV, false, GL>(p, src, dst, grid, smem, st);
+    if (p.ir == 10) {
+        if (p.glog == 2) { R8B_F2_CASE(10, 2) } else if (p.glog == 1) { R8B_F2_CASE(10, 1) } else { R8B_F2_CASE(10, 0) }
+    } else {
+        if (p.glog == 2) { R8B_F2_CASE(8, 2) } else if (p.glog == 1) { R8B_F2_CASE(8, 1) } else { R8B_F2_CASE(8, 0) }
+    }
+#undef R8B_F2_CASE
+}
+
+} // namespace r8bgpu

@@ -1,0 +1,279 @@
+// r8b_fused2_core.cuh -- per-thread phase functions of the v2 fused kernel (r8b_fused2.cu).
+//
+// Same operator as r8b_fused.cu -- 2x BlockConvolver (CDSPBlockConvolver.h:252-354 on top of
+// CDSPRealFFT.h:98-385) followed by the whole-stepping fractional interpolator
+// (CDSPFracInterpolator.h:991-1060) -- but one TILE per 256-thread half-CTA instead of one tile PAIR per
+// 512-thread CTA, so that two tiles in different phases share an SM:
+//
+//   forward : real input x[w .. w+4096)  ->  z[m] = x[2m] + i x[2m+1]  ->  2048-point complex DIF FFT
+//             (radix 8 from registers, then radix 16, 16; spectrum in slot order)
+//   C       : X[k] = E[k] + W_M^k O[k] from (Z[k], Z[N-k]);  Y = X * G on all 4096 bins (X Hermitian),
+//             G = FFT(g_0 + i g_1)/(2M) the polyphase-packed low-pass (same table as v1)
+//   inverse : 4096-point complex, radix 16 x 3; element e of the result = y[2(w+e)] + i y[2(w+e)+1]
+//   interp  : out[j] = sum_i bank[phase(j)][i] * y[p_j - fll + i] out of shared memory
+//
+// Every function takes the thread's index explicitly and touches only its arguments, so the same code
+// runs on the host, one "thread" after another, in tests/cpp/fused2_emul.cu (barriers = loop boundaries).
+#pragma once
+#include <climits>
+
+#include "r8b_fused_common.cuh"
+
+namespace r8bgpu {
+namespace f2 {
+
+constexpr int FN = 2048;   // complex length of the forward transform (real length FM = 4096)
+constexpr int HT = 256;    // threads of one half-CTA pipeline
+constexpr int IQ2 = 3;     // stepping cycles per lane in the interpolation register tile
+
+struct Tile {
+    int ch;
+    long long A0, A1;      // owned 2x-rate positions [A0, A1)
+    long long w;           // input index of local sample 0 of the FFT window
+};
+
+R8B_HD Tile tile_of(const FusedParams& p, int u)
+{
+    Tile t;
+    t.ch = u / p.n_tiles;
+    const int ti = u - t.ch * p.n_tiles;
+    t.A0 = p.p_lo + (long long) ti * p.span;
+    t.A1 = t.A0 + p.span;
+    if (t.A1 > p.p_hi) t.A1 = p.p_hi;
+    // valid y of the tile starts at A0 - yl (even) = 2 * (first valid m); the window starts lg earlier
+    t.w = (t.A0 - p.yl) / 2 - p.lg;
+    return t;
+}
+
+// Which way the tile's 4096 input samples arrive: 0 = every sample individually (history ring, or past
+// the available input), 1 = plain loads from the caller's block, 2 = one bulk copy (16-byte aligned run).
+R8B_HD int tile_input_path(const SrcView& src, const Tile& t)
+{
+    if (!(t.w >= src.cur_base && t.w + FM <= src.avail)) return 0;
+    const double* a = src.cur + (long long) t.ch * src.cur_stride + (t.w - src.cur_base);
+    return (reinterpret_cast<unsigned long long>(a) & 15) == 0 ? 2 : 1;
+}
+
+// z[m], m = r + 256 j, straight from global memory (paths 0 and 1)
+R8B_HD void gather_tile(double2 (&v)[8], const SrcView& src, const Tile& t, int path, int r)
+{
+    if (path != 0) {
+        const double* __restrict__ a = src.cur + (long long) t.ch * src.cur_stride + (t.w - src.cur_base) + 2 * r;
+        if ((reinterpret_cast<unsigned long long>(a) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = R8B_LDG(reinterpret_cast<const double2*>(a + 512 * j));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = make_double2(R8B_LDG(a + 512 * j), R8B_LDG(a + 512 * j + 1));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const long long n = t.w + 2 * (r + 256 * j);
+            v[j] = make_double2(src_read_f(src, t.ch, n), src_read_f(src, t.ch, n + 1));
+        }
+    }
+}
+
+// forward pass 1: radix 8 on registers, NCUR = FN, D = 256; twiddle W_2048^(r q) = W_4096^(r 2q)
+R8B_HD void fwd_pass1_r8(double2 (&v)[8], double2* __restrict__ s, const double2* __restrict__ twc,
+                         const double2* __restrict__ twf, int r)
+{
+    Network<8, +1>::run(v);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        double2 x = v[bitrev<8>(q)];
+        if (q > 0) x = cmul<+1>(x, tw_pair(twc, twf, r, 2 * q));
+        s[fft_pad(r + q * 256)] = x;
+    }
+}
+
+// C, first half: this thread's four frequency pairs (k, N-k), k <= N/2.  In slot order (k = q1 + 8 q2 + 128 q3,
+// slot = 256 q1 + 16 q2 + q3) those are the slots with q3 < 8; a thread takes runs of 8 consecutive slots.
+R8B_HD int c_freq(int ht, int u) { return freq_of<FN>(16 * ((ht >> 3) + 32 * u) + (ht & 7)); }
+
+R8B_HD void c_load(const double2* __restrict__ buf, int ht, double2 (&z1)[4], double2 (&z2)[4])
+{
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int s1 = 16 * ((ht >> 3) + 32 * u) + (ht & 7);
+        const int k = freq_of<FN>(s1);
+        const int s2 = slot_of<FN>((FN - k) & (FN - 1));
+        z1[u] = buf[fft_pad(s1)];
+        z2[u] = buf[fft_pad(s2)];
+    }
+}
+
+// C, second half (after every thread has fetched its Z values: the products overwrite them).
+//   A' = Z[k] + conj Z[N-k] = 2 E[k],  B' = -i (Z[k] - conj Z[N-k]) = 2 O[k]
+//   2X[k] = A' + W^k B',  2X[k+N] = A' - W^k B',  X[N-k] = conj X[k+N],  X[M-k] = conj X[k]
+// (the factor 2 lives in G).  k = 0 and k = N/2 pair with themselves; their four stores collapse to two
+// locations written with equal values.
+R8B_HD void c_pair(const FusedParams& p, double2* __restrict__ buf, int k, double2 z1, double2 z2)
+{
+    const double2 a = make_double2(z1.x + z2.x, z1.y - z2.y);
+    const double2 b = make_double2(z1.y + z2.y, z2.x - z1.x);
+    const double2 wb = cmul<+1>(b, R8B_LDG(&p.tw[k]));
+    const double2 x0 = make_double2(a.x + wb.x, a.y + wb.y);
+    const double2 x1 = make_double2(a.x - wb.x, a.y - wb.y);
+    const int s0 = slot_of<FM>(k), s1 = slot_of<FM>(k + FN), s2 = slot_of<FM>(FN - k), s3 = slot_of<FM>((FM - k) & (FM - 1));
+    buf[fft_pad(s0)] = cmul<+1>(x0, R8B_LDG(&p.spec[s0]));
+    buf[fft_pad(s1)] = cmul<+1>(x1, R8B_LDG(&p.spec[s1]));
+    buf[fft_pad(s2)] = cmul<+1>(make_double2(x1.x, -x1.y), R8B_LDG(&p.spec[s2]));
+    buf[fft_pad(s3)] = cmul<+1>(make_double2(x0.x, -x0.y), R8B_LDG(&p.spec[s3]));
+}
+
+// inverse, last pass (NCUR = M, D = 256): loads + butterfly; the results leave through y_store()
+R8B_HD void inv3_load(const double2* __restrict__ buf, const double2* __restrict__ twc, const double2* __restrict__ twf,
+                      int g, double2 (&v)[16])
+{
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        double2 x = buf[fft_pad(g + q * 256)];
+        if (q > 0) x = cmul<-1>(x, tw_pair(twc, twf, g, q));
+        v[q] = x;
+    }
+    Network<16, -1>::run(v);
+}
+
+template <bool PADV>
+R8B_HD void y_store(double2* __restrict__ buf, const double2 (&v)[16], int g, long long w, int ysh)
+{
+    double* yb = reinterpret_cast<double*>(buf);
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int e = g + j * 256;              // local input-rate position
+        double2 x = v[bitrev<16>(j)];
+        if (2 * (w + e) < 0) x = make_double2(0.0, 0.0); // the reference's interpolator starts from silence
+        if (!PADV) {
+            reinterpret_cast<double2*>(yb)[e] = x;
+        } else {
+            yb[ylay(2 * e, ysh)] = x.x;
+            yb[ylay(2 * e + 1, ysh)] = x.y;
+        }
+    }
+}
+
+// Tile-level bookkeeping of the interpolation, by ONE thread while the transforms run: everything the
+// per-task code needs afterwards is 32-bit and relative to the tile.
+//   s_i[0] outputs of the tile, [1] last (shifted) stepping cycle, [2] output index of (cycle 0, phase 0)
+//   relative to the tile's first output, [3] y index of the window of (cycle 0, offset 0)
+R8B_HD void interp_prepare(const FusedParams& p, const DstView& dst, const Tile& t, int* s_i, double** s_op)
+{
+    long long ja = (t.A0 * p.out_step + p.in_step - 1) / p.in_step;
+    long long jb = (t.A1 * p.out_step + p.in_step - 1) / p.in_step;
+    if (ja < p.e0) ja = p.e0;
+    if (jb > p.e1) jb = p.e1;
+    const long long ad = ja - p.delta, bd = jb - 1 - p.delta;
+    const long long c_first = ad >= 0 ? ad / p.out_step : -1, c_last = bd >= 0 ? bd / p.out_step : -1;
+    s_i[0] = jb > ja ? (int) (jb - ja) : 0;
+    s_i[1] = (int) (c_last - c_first);
+    s_i[2] = (int) (c_first * p.out_step - ja);
+    s_i[3] = (int) (c_first * p.in_step - p.fll - 2 * t.w);
+    *s_op = dst.ptr + (long long) t.ch * dst.stride + ((ja - dst.base) & dst.mask);
+}
+
+// Lane geometry of the interpolation: a warp covers CL = 32 >> GLOG stepping cycles x GL = 1 << GLOG phase
+// groups per instruction; a lane owns IR consecutive phases of its group in IQ2 cycles (CL apart).
+template <int IR, int GLOG>
+struct TaskGeom {
+    static constexpr int GL = 1 << GLOG, CL = 32 >> GLOG, CYC = CL * IQ2;
+    int grp, r0, o0, cb;   // phase group (clamped), its first phase, its window offset, first cycle of the lane
+    bool gvalid;
+    R8B_HD void set(const FusedParams& p, const int* __restrict__ s_goff, int task, int lane)
+    {
+        const int n_groups = (p.out_step + IR - 1) / IR;
+        const int n_gt = (n_groups + GL - 1) / GL;
+        const int gt = task % n_gt, chunk = task / n_gt;
+        grp = gt * GL + (lane >> (5 - GLOG));
+        gvalid = grp < n_groups;
+        if (!gvalid) grp = n_groups - 1;
+        r0 = p.delta + grp * IR;
+        o0 = s_goff[grp];
+        cb = chunk * CYC + (lane & (CL - 1));
+    }
+    static R8B_HD int n_tasks(const FusedParams& p, int c_cnt)
+    {
+        const int n_groups = (p.out_step + IR - 1) / IR;
+        return ((n_groups + GL - 1) / GL) * ((c_cnt + CYC) / CYC);
+    }
+};
+
+// y indices of the lane's IQ2 windows (clamped into the tile: clamped lanes never store)
+template <int IR, int GLOG>
+R8B_HD void interp_windows(const FusedParams& p, const TaskGeom<IR, GLOG>& g, const int* __restrict__ s_i, int (&yo)[IQ2])
+{
+    const int c_cnt = s_i[1], wbase = s_i[3];
+#pragma unroll
+    for (int q = 0; q < IQ2; q++) {
+        int c = g.cb + q * TaskGeom<IR, GLOG>::CL;
+        if (c > c_cnt) c = c_cnt;
+        int li = c * p.in_step + g.o0 + wbase;
+        if (li < 0) li = 0;
+        if (li > 2 * FM - p.smaxp) li = 2 * FM - p.smaxp;
+        yo[q] = li;
+    }
+}
+
+// The tap loop: group bank [smaxp][IR] (phase r's filter pre-shifted by its window offset and zero-padded,
+// so there are no predicates and one base address), IR x IQ2 accumulators.
+template <int IR, bool PADV>
+R8B_HD void interp_acc(const double* __restrict__ yb, const double* __restrict__ gb, const int (&yo)[IQ2], int smaxp, int ysh,
+                       double (&acc)[IR][IQ2])
+{
+#pragma unroll
+    for (int r = 0; r < IR; r++)
+#pragma unroll
+        for (int q = 0; q < IQ2; q++) acc[r][q] = 0.0;
+#pragma unroll 4
+    for (int s = 0; s < smaxp; s++) {
+        double yv[IQ2];
+#pragma unroll
+        for (int q = 0; q < IQ2; q++) yv[q] = PADV ? yb[ylay(yo[q] + s, ysh)] : yb[yo[q] + s];
+#pragma unroll
+        for (int r = 0; r < IR; r += 2) {
+            const double2 b = *reinterpret_cast<const double2*>(gb + s * IR + r);
+#pragma unroll
+            for (int q = 0; q < IQ2; q++) {
+                acc[r][q] = fma(b.x, yv[q], acc[r][q]);
+                acc[r + 1][q] = fma(b.y, yv[q], acc[r + 1][q]);
+            }
+        }
+    }
+}
+
+// Stores straight from the lane's registers (any IR, ring or linear destination).
+template <int IR, int GLOG>
+R8B_HD void interp_store_direct(const FusedParams& p, const DstView& dst, int ch, const TaskGeom<IR, GLOG>& g,
+                                const int* __restrict__ s_i, double* s_o, const double (&acc)[IR][IQ2])
+{
+    const int n_j = s_i[0], c_cnt = s_i[1], jshift = s_i[2];
+    if (!g.gvalid) return;
+#pragma unroll
+    for (int q = 0; q < IQ2; q++) {
+        const int c = g.cb + q * TaskGeom<IR, GLOG>::CL;
+        if (c > c_cnt) continue;
+        const int j0 = c * p.out_step + g.r0 + jshift; // relative to the tile's first output
+        const bool full = (p.wrap || g.r0 + IR <= p.out_step) && j0 >= 0 && j0 + IR <= n_j;
+        if (dst.mask == -1) {
+            double* o = s_o + j0;
+            if (full && (reinterpret_cast<unsigned long long>(o) & 15) == 0) {
+#pragma unroll
+                for (int r = 0; r < IR; r += 2) *reinterpret_cast<double2*>(o + r) = make_double2(acc[r][q], acc[r + 1][q]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < IR; r++)
+                    if ((p.wrap || g.r0 + r < p.out_step) && j0 + r >= 0 && j0 + r < n_j) o[r] = acc[r][q];
+            }
+        } else { // ring destination (another stage follows): s_o is the ring slot of the tile's first output
+            double* const rb = dst.ptr + (long long) ch * dst.stride;
+            const long long i0 = (s_o - rb) + (long long) j0;
+#pragma unroll
+            for (int r = 0; r < IR; r++)
+                if ((p.wrap || g.r0 + r < p.out_step) && j0 + r >= 0 && j0 + r < n_j) rb[(i0 + r) & dst.mask] = acc[r][q];
+        }
+    }
+}
+
+} // namespace f2
+} // namespace r8bgpu

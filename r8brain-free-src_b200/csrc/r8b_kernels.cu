@@ -170,13 +170,7 @@ static void launch_bc_inst(const BlockConvParams& p, const SrcView& src, const D
 {
     constexpr int NT = 256;
     const int smem = blockconv_smem_bytes(p.fft_log2, UP);
-    static bool configured[16] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 16 && !configured[dev]) {
-        cudaFuncSetAttribute(k_blockconv<M, UP, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured[dev] = true;
-    }
+    ensure_dyn_smem<k_blockconv<M, UP, NT>>(smem);
     const int n_pairs = (p.n_tiles + 1) >> 1;
     k_blockconv<M, UP, NT><<<(unsigned) (n_pairs * n_ch), NT, smem, st>>>(p, src, dst);
 }
@@ -609,13 +603,7 @@ void launch_hbup_cascade(const HbCascadeParams& p, int smem_bytes, const SrcView
                          int n_ch, cudaStream_t st)
 {
     if (p.n_tiles <= 0 || n_ch <= 0) return;
-    static bool configured[16] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 16 && !configured[dev]) {
-        cudaFuncSetAttribute(k_hbup_cascade, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        configured[dev] = true;
-    }
+    ensure_dyn_smem<k_hbup_cascade>(220 * 1024);
     dim3 grid((unsigned) p.n_tiles, (unsigned) n_ch);
     k_hbup_cascade<<<grid, HB_NT, smem_bytes, st>>>(p, src, dst);
 }

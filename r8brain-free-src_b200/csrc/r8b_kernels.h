@@ -2,7 +2,22 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 namespace r8bgpu {
+
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per (kernel, device): thread-safe, and
+// devices beyond the bitmap simply set the attribute on every launch.
+template <auto Kernel>
+inline void ensure_dyn_smem(int bytes)
+{
+    static std::atomic<unsigned long long> done[4];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 256 && ((done[dev >> 6].load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) return;
+    cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (dev >= 0 && dev < 256) done[dev >> 6].fetch_or(1ull << (dev & 63), std::memory_order_release);
+}
 
 // A per-channel sample stream addressed by ABSOLUTE sample index n (n = 0 is the first sample
 // after clear()).  Samples with n >= cur_base are read from the caller's block of this
@@ -126,6 +141,11 @@ struct FusedParams {
                              // banks apart -- lanes that sit on different rows then load without bank conflicts
     int poly_n;              // > 0: input positions advance by ~poly_n per output; threads take 4 consecutive outputs
     int poly_chunks;         // a pair's outputs are processed in this many pieces, each with its own run (>= 1)
+    // v2 kernel (r8b_fused2.cu): persistent CTAs, one tile per half-CTA
+    int n_ch;                // channels of this launch (work units = n_ch * n_tiles)
+    int glog;                // log2 of the phase groups a warp covers per instruction (lanes = 32>>glog cycles x 1<<glog groups)
+    int flags;               // bit 0: ping-pong token around the interpolation, bit 1: bulk-copy input tiles
+    const double2* tw_tab;   // 512 entries: tw2t[q*16+r] = W_256^(r q), then tw1t[q*16+r] = W_M^(r q)
 };
 int fused_smem_bytes(int bank_doubles_in_smem);
 int fused_max_span(int lg, int yl, int yr);
@@ -133,6 +153,9 @@ int fused_stage_doubles();
 int fused_fixed_doubles();
 int fused_poly_queue_bytes();
 void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st);
+int fused2_smem_bytes(int bank_doubles, bool staged);
+int fused2_stage_off(int bank_doubles);
+void launch_up2_frac2(const FusedParams& p, const SrcView& src, const DstView& dst, int n_sm, cudaStream_t st);
 
 int blockconv_smem_bytes(int fft_log2, int up);
 cudaError_t blockconv_configure(); // opt-in shared memory attributes; call once per device

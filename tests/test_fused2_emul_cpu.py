@@ -1,0 +1,89 @@
+"""CPU: the v2 fused kernel's own arithmetic, run thread by thread on the host, against the oracle.
+
+csrc/r8b_fused2_core.cuh holds the per-thread phase functions of k_up2_frac2 (real-input FFT split, slot orders,
+spectrum multiply, inverse passes, interpolation bookkeeping); they compile for the host.  tests/cpp/fused2_emul.cpp
+drives them with the engine's own host code (plan, schedule, tables, tile geometry).  What this cannot see is the
+device-only part: barriers, bulk copies and the transposed store staging -- those are covered by the GPU parity tests.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(ROOT, "r8brain-free-src_b200", "csrc")
+EPS = 2.0 ** -52
+
+
+def _cuda_include():
+    for d in (os.environ.get("CUDA_HOME"), "/usr/local/cuda"):
+        if d and os.path.exists(os.path.join(d, "include", "cuda_runtime.h")):
+            return os.path.join(d, "include")
+    return None
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    inc = _cuda_include()
+    if inc is None:
+        pytest.skip("CUDA headers not found")
+    so = str(tmp_path_factory.mktemp("f2emul") / "libf2emul.so")
+    srcs = [os.path.join(HERE, "cpp", "fused2_emul.cpp")] + [os.path.join(CSRC, f) for f in
+                                                             ("r8b_plan.cpp", "r8b_design.cpp", "r8b_hosttab.cpp")]
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I" + inc, "-o", so] + srcs, check=True)
+    L = C.CDLL(so)
+    L.f2emul_create.restype = C.c_void_p
+    L.f2emul_create.argtypes = [C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int]
+    L.f2emul_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.f2emul_destroy.argtypes = [C.c_void_p]
+    return L
+
+
+def _run(L, src, dst, max_len, lens, glog=-1, atten=180.15, tb=2.0, seed=7):
+    ref = oracle_util.best_oracle()
+    h = L.f2emul_create(src, dst, max_len, tb, atten, glog)
+    assert h, "rate pair does not plan to BlockConv(2x) -> whole-stepping interpolator"
+    rs = ref.Resampler(src, dst, max_len, tb, atten)
+    rng = np.random.default_rng(seed)
+    worst = se = sy = 0.0
+    total = 0
+    for n in lens:
+        x = rng.uniform(-1.0, 1.0, n)
+        out = np.zeros(int(n * dst / src * 1.25) + 4096)
+        k = L.f2emul_process(h, x.ctypes.data, n, out.ctypes.data, len(out))
+        yr = rs.process(x)
+        assert k == len(yr), (k, len(yr))
+        if k:
+            d = out[:k] - yr
+            worst = max(worst, float(np.max(np.abs(d))) / float(np.max(np.abs(yr))))
+            se += float(np.sum(d * d))
+            sy += float(np.sum(yr * yr))
+            total += k
+    L.f2emul_destroy(h)
+    assert total > 0
+    assert worst <= 32 * EPS, worst / EPS
+    assert (se / sy) ** 0.5 <= 4 * EPS, (se / sy) ** 0.5 / EPS
+
+
+@pytest.mark.parametrize("glog", [0, 1, 2])
+def test_cfg2_chain_all_lane_splits(emul, glog):
+    _run(emul, 44100.0, 96000.0, 8192, [8192, 8192, 8192], glog=glog)
+
+
+def test_ragged_blocks_history_ring_and_misaligned_rows(emul):
+    # odd lengths shift the block base parity (plain-load path), tiny and empty blocks reach into the history ring
+    _run(emul, 44100.0, 96000.0, 8192, [1, 0, 4097, 777, 8192, 3, 8191, 5000])
+
+
+def test_downsampling_chain_padded_y_layout(emul):
+    _run(emul, 48000.0, 44100.0, 8191, [8191, 8191, 4000])   # in_step 320: padded y layout, 10-phase groups
+
+
+def test_full_block_and_presets(emul):
+    _run(emul, 44100.0, 96000.0, 65536, [65536, 65536])
+    _run(emul, 44100.0, 48000.0, 4096, [4096] * 4, atten=136.45)
