@@ -473,7 +473,7 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 b->dev_bytes += B.gb.size() * sizeof(double);
                 d.bank_in_smem = (fused_smem_bytes(d.gbank_smem_len) <= 220 * 1024) ? 1 : 0;
                 // the persistent two-pipeline kernel needs the call's whole bank in shared memory
-                if (d.fused_into_prev && i > 0 && fused2_smem_bytes(d.gbank_smem_len, false) <= 227 * 1024 &&
+                if (d.fused_into_prev && i > 0 && fused2_smem_bytes(d.gbank_smem_len, false) <= kFused2SmemMax &&
                     (s.out_step + d.ir - 1) / d.ir <= 192 && !getenv("R8BGPU_FUSED_V1"))
                     b->dev[i - 1].f2_ok = true;
             }
@@ -806,7 +806,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.n_ch = nch;
                 p.flags = b->f2_flags;
                 p.tw_tab = d.tw_tab;
-                p.stage_off = (p.ir == 8 && fused2_smem_bytes(p.gbank_smem_len, true) <= 227 * 1024 && !getenv("R8BGPU_NO_STAGE"))
+                p.stage_off = (p.ir == 8 && fused2_smem_bytes(p.gbank_smem_len, true) <= kFused2SmemMax && !getenv("R8BGPU_NO_STAGE"))
                                   ? fused2_stage_off(p.gbank_smem_len) : 0;
                 p.glog = fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
                 launch_up2_frac2(p, src, dst, b->n_sm, st);

@@ -1,6 +1,7 @@
 // r8b_design.cpp -- see r8b_design.h.  Strict-IEEE host code (build with -ffp-contract=off).
 #include "r8b_design.h"
 
+#include <climits>
 #include <cmath>
 #include <cstring>
 
@@ -211,58 +212,58 @@ bool design_lowpass(double norm_freq, double trans_band, double req_atten, doubl
 
 namespace {
 
-// One fractional-delay windowed-sinc row (CDSPSincFilterGen.h:452-552) with Kaiser window raised
-// to `wpow`, written with stride `stride`; then DC-normalised (r8bbase.h:934-961).
-void frac_delay_row(double* op, int stride, int filter_len, double len2, double frac_delay,
-                    double beta, double wpow)
+// One fractional-delay windowed-sinc row, evaluated tap by tap in closed form.
+//
+// Operator (what CDSPSincFilterGen.h:452-552 computes with running state): for tap position
+// t = -fl2 .. fl2-1 and u = t + fd,
+//     row[t] = 0                                   if u lies outside [-len2, len2]   (only the edge taps can)
+//            = w(t)^wpow                           where u is a zero of the sinc argument
+//                                                  (fd ~ 0 at t = 0, fd ~ 1 at t = -1: the 0/0 limit)
+//            = (-1)^t * sin(pi fd)/pi * w(t)^wpow / u   everywhere else,
+// w(t) = Kaiser window at (t + fd)/len2.  sin(pi (t+fd)) = (-1)^t sin(pi fd) is what makes one sine enough.
+// The row is then DC-normalised by its plain left-to-right sum (r8bbase.h:934-961).  Each value is
+// produced by the same operations in the same order as the reference, which keeps the bank bit-exact
+// (tests/test_host_cpu.py::test_frac_banks_and_halfbands_bit_exact).
+struct FracRow {
+    double len2, fd, beta, mul, wpow, sinc_gain;
+    int fl2, unit_tap; // unit_tap: the tap that carries the pure window value, or INT_MIN
+
+    FracRow(double len2_, double frac_delay, double beta_, double wpow_) : len2(len2_), fd(frac_delay), wpow(wpow_)
+    {
+        fl2 = (int) std::ceil(len2); // CDSPSincFilterGen.h:168-176
+        beta = beta_ < 1.0 ? 1.0 : (beta_ > 350.0 ? 350.0 : beta_);
+        mul = 1.0 / bessel_i0(beta);
+        sinc_gain = std::sin(fd * kPi) / kPi;
+        const double kTiny = 2.3e-13; // the reference's threshold for "fd is an integer"
+        unit_tap = std::fabs(fd - 1.0) < kTiny ? -1 : (std::fabs(fd) < kTiny ? 0 : INT_MIN);
+    }
+    double window(int t) const
+    {
+        const double n = 1.0 - sq(t * (1.0 / len2) + fd * (1.0 / len2));
+        return n <= 0.0 ? 0.0 : bessel_i0(beta * std::sqrt(n)) * mul;
+    }
+    double tap(int t) const
+    {
+        const double u = t + fd;
+        if ((t == -fl2 && u < -len2) || (t == fl2 - 1 && u > len2)) return 0.0;
+        const double w = pow_abs(window(t), wpow);
+        if (t == unit_tap) return w;
+        const double s = (t & 1) ? -sinc_gain : sinc_gain;
+        return s * w / u;
+    }
+};
+
+void frac_delay_row(double* op, int stride, int filter_len, double len2, double frac_delay, double beta, double wpow)
 {
-    const int fl2 = (int) std::ceil(len2); // initFrac: CDSPSincFilterGen.h:168-176
-    KaiserWindow win;
-    win.init(beta, len2, -fl2, frac_delay);
-    const double fd = frac_delay;
-    double* p = op;
-    int t = -fl2;
-
-    if (t + fd < -len2) {
-        win.next();
-        *p = 0.0;
-        p += stride;
-        t++;
+    const FracRow row(len2, frac_delay, beta, wpow);
+    double sum = 0.0;
+    for (int i = 0; i < filter_len; i++) {
+        const double v = row.tap(i - row.fl2);
+        op[(size_t) i * stride] = v;
+        sum += v;
     }
-
-    double f = std::sin(fd * kPi) / kPi;
-    if ((t & 1) != 0) f = -f;
-
-    int is_zero_x = (std::fabs(fd - 1.0) < 2.3e-13);
-    int mt = 0 - is_zero_x;
-    is_zero_x = (is_zero_x || std::fabs(fd) < 2.3e-13);
-
-    while (t < mt) {
-        *p = f * pow_abs(win.next(), wpow) / (t + fd);
-        p += stride;
-        t++;
-        f = -f;
-    }
-    if (is_zero_x) *p = pow_abs(win.next(), wpow);
-    else *p = f * pow_abs(win.next(), wpow) / fd;
-
-    mt = fl2 - 2;
-    while (t < mt) {
-        p += stride;
-        t++;
-        f = -f;
-        *p = f * pow_abs(win.next(), wpow) / (t + fd);
-    }
-    p += stride;
-    t++;
-    f = -f;
-    const double ut = t + fd;
-    *p = (ut > len2 ? 0.0 : f * pow_abs(win.next(), wpow) / ut);
-
-    double s = 0.0;
-    for (int i = 0; i < filter_len; i++) s += op[(size_t) i * stride];
-    s = 1.0 / s;
-    for (int i = 0; i < filter_len; i++) op[(size_t) i * stride] *= s;
+    const double norm = 1.0 / sum;
+    for (int i = 0; i < filter_len; i++) op[(size_t) i * stride] *= norm;
 }
 
 } // namespace
@@ -343,25 +344,26 @@ HalfbandTaps select_halfband(double req_atten, int steep_index, bool is_third)
 
 bool whole_stepping(double src_rate, double dst_rate, int& in_step, int& out_step)
 {
-    // Subtractive Euclid on doubles, at most 149 steps (CDSPFracInterpolator.h:609-628).
-    double l = src_rate, s = dst_rate, gcd = 0.0;
-    bool found = false;
-    for (int it = 1; it < 150; it++) {
-        const double r = l - s;
-        if (r == 0.0) {
-            gcd = s;
-            found = s > 0.0;
-            break;
-        }
-        l = s;
-        s = std::fabs(r);
+    // The interpolator steps by whole bank rows when Src/Dst reduces to InStep/OutStep with a small OutStep.
+    // The reference looks for the common divisor on the doubles themselves and gives up after a fixed budget
+    // of 149 equality checks, i.e. 148 reduction steps (CDSPFracInterpolator.h:609-628), then rejects OutStep > 1500 (:664-670); both
+    // limits decide which rates take the order-2 bank instead, so they are part of the plan and kept as
+    // explicit guards.  Differences of exactly representable rates are exact, so this is Euclid's
+    // subtractive algorithm on the pair (larger, smaller) = (a, b) -> (b, |a - b|).
+    constexpr int kMaxReductions = 148, kMaxOutStep = 1500;
+    double a = src_rate, b = dst_rate;
+    int reductions = 0;
+    while (a != b) {
+        if (++reductions > kMaxReductions) return false;
+        const double d = std::fabs(a - b);
+        a = b;
+        b = d;
     }
-    if (!found) return false;
-    const double a = src_rate / gcd, b = dst_rate / gcd;
-    in_step = (int) a;
-    out_step = (int) b;
-    if (a != in_step || b != out_step) return false;
-    if (out_step > 1500) return false; // :664-670
+    if (!(b > 0.0)) return false;
+    const double qi = src_rate / b, qo = dst_rate / b;
+    if (qi != std::floor(qi) || qo != std::floor(qo) || qi > 2147483647.0 || qo > (double) kMaxOutStep) return false;
+    in_step = (int) qi;
+    out_step = (int) qo;
     return true;
 }
 

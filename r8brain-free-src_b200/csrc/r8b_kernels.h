@@ -15,7 +15,14 @@ inline void ensure_dyn_smem(int bytes)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 256 && ((done[dev >> 6].load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) return;
-    cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    // the opt-in limit (227 KB per CTA on sm_100) covers static + dynamic shared memory together
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, Kernel) == cudaSuccess && bytes > 227 * 1024 - (int) fa.sharedSizeBytes)
+        bytes = 227 * 1024 - (int) fa.sharedSizeBytes;
+    if (cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return; // not marked done: the launch reports the error
+    }
     if (dev >= 0 && dev < 256) done[dev >> 6].fetch_or(1ull << (dev & 63), std::memory_order_release);
 }
 
@@ -153,6 +160,7 @@ int fused_stage_doubles();
 int fused_fixed_doubles();
 int fused_poly_queue_bytes();
 void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st);
+constexpr int kFused2SmemMax = 227 * 1024 - 1024; // dynamic part; the kernel's static shared memory is < 1 KB
 int fused2_smem_bytes(int bank_doubles, bool staged);
 int fused2_stage_off(int bank_doubles);
 void launch_up2_frac2(const FusedParams& p, const SrcView& src, const DstView& dst, int n_sm, cudaStream_t st);

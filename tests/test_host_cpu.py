@@ -174,3 +174,22 @@ def test_fasttiming_scheduler_matches_reference(pkg):
         r = ref_ft.Resampler(src, dst, 4096, 2.0, pkg.ATTEN_24)
         x = np.zeros(4096)
         assert plan.simulate(lens) == [len(r.process(x[:l])) for l in lens]
+
+
+@pytest.mark.skipif(not ou.have_ref('e0'), reason='compiled reference not present')
+def test_whole_stepping_decision_matches_reference(pkg):
+    """Whole-stepping vs order-2 bank is decided by a bounded subtractive GCD on the doubles
+    (CDSPFracInterpolator.h:609-673): the iteration budget and the OutStep limit are part of the plan."""
+    ref = ou.RefOracle("e0")
+    pairs = [(float(n), 1.0) for n in range(1, 160)] + [(1.0, float(n)) for n in range(1, 160)]
+    pairs += [(float(a), float(b)) for a in (147, 148, 149, 150, 151, 233, 377, 1499, 1500, 1501, 1502, 3001)
+              for b in (1, 2, 3, 89, 144, 1500, 1501, 2999)]
+    pairs += [(44100.0, 96000.0), (48000.0, 47999.0), (44100.5, 96000.0), (0.1, 0.3), (96000.0, 88200.0)]
+    for src, dst in pairs:
+        if src == dst:
+            continue
+        ok, a, b = ref.whole_stepping(src, dst)
+        st = pkg.Plan.single_stage(1, [src, dst, 180.15, 0], 1024).stages()[0]
+        assert (st["order"] == 0) == ok, (src, dst, ok, st)
+        if ok:
+            assert (st["in_step"], st["out_step"]) == (a, b), (src, dst, a, b, st)
