@@ -40,7 +40,11 @@ WORKLOADS = {
     "cfg4_128ch_44100_2822400_r24_extfft": (44100.0, 2822400.0, 180.15, 2.0, 1, 128),
     "cfg3b_1024ch_192000_44100_r24": (192000.0, 44100.0, 180.15, 2.0, 0, 1024),
 }
+# algorithmic flops per input sample (real-FFT 2.5 N log2 N per block + interpolation / half-band MACs)
+FLOPS_PER_IN_SAMPLE = {"cfg2_1024ch_44100_96000_r24": 241.0, "cfg3_1024ch_48000_44100_r24": 188.0,
+                       "cfg5_512ch_48000_47999_r24": 281.0, "cfg4_128ch_44100_2822400_r24_extfft": 855.0}
 DEFAULT_WORKLOAD = "cfg2_1024ch_44100_96000_r24"
+CPU_KEYS = ("value", "unit", "cores", "kind", "sample", "per_core", "sample_channels", "single_thread")
 BLOCK = 65536
 
 
@@ -105,6 +109,30 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU baseline may use: the affinity mask, capped by a cgroup CPU quota if one is set."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                t = f.read().split()
+            if path.endswith("cpu.max"):
+                if t[0] != "max":
+                    n = min(n, max(1, int(float(t[0]) / float(t[1]))))
+            else:
+                q = int(t[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                        n = min(n, max(1, q // int(f.read())))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def synth_block(n_ch, block, seed):
     """Planar fp64 white noise in [-1,1), per-channel stream."""
     import numpy as np
@@ -112,7 +140,7 @@ def synth_block(n_ch, block, seed):
     return rng.uniform(-1.0, 1.0, size=(n_ch, block))
 
 
-def cpu_reference_run(src, dst, tb, atten, extfft, threads, target_seconds=8.0):
+def cpu_reference_run(src, dst, tb, atten, extfft, threads, target_seconds=8.0, single_thread=True):
     """Time the compiled reference (oracle/_ref) on host cores over a bounded sample."""
     import oracle_util as ou
     flavor = ("e1" if extfft else "e0") + ("_fast" if ou.cpu_supports_fast() and ou.have_ref(("e1" if extfft else "e0") + "_fast") else "")
@@ -123,12 +151,45 @@ def cpu_reference_run(src, dst, tb, atten, extfft, threads, target_seconds=8.0):
     x = synth_block(n_ch, BLOCK, 99)
     # calibrate with 1 call, then size the sample to ~target_seconds of wall time
     t1, _, _ = ref.bench(src, dst, BLOCK, tb, atten, x, 1, 1, threads)
-    calls = int(max(2, min(256, target_seconds / max(t1, 1e-4))))
+    calls = int(max(2, min(8192, target_seconds / max(t1, 1e-4))))
     secs, n_out, _ = ref.bench(src, dst, BLOCK, tb, atten, x, 1, calls, threads)
     val = 1e-6 * n_ch * BLOCK * calls / secs
-    return {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "reference",
-            "sample": "%d ch x %d calls x %d frames, %s, %d threads, %.2f s" % (n_ch, calls, BLOCK, ref.name, threads, secs),
-            "ms_per_step_equiv": secs / calls * 1e3, "n_ch": n_ch, "calls": calls, "secs": secs}
+    res = {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "reference",
+           "sample": "%d ch x %d calls x %d frames, %s, %d threads, %.2f s" % (n_ch, calls, BLOCK, ref.name, threads, secs),
+           "per_core": val / max(1, threads), "sample_channels": n_ch, "calls": calls, "secs": secs,
+           "sample_ms_per_call": secs / calls * 1e3}
+    if single_thread:
+        # BASELINE configs[0]: one channel, one thread (what example.cpp / README.md:111-114 quote per core)
+        t1, _, _ = ref.bench(src, dst, BLOCK, tb, atten, x[:1], 1, 1, 1)
+        c1 = int(max(2, min(2048, 2.0 / max(t1, 1e-4))))
+        s1, _, _ = ref.bench(src, dst, BLOCK, tb, atten, x[:1], 1, c1, 1)
+        res["single_thread"] = {"value": 1e-6 * BLOCK * c1 / s1, "unit": "Msamples/s", "cores": 1,
+                                "sample": "1 ch x %d calls x %d frames, %s, %.2f s" % (c1, BLOCK, ref.name, s1)}
+    return res
+
+
+def verify_against_oracle(src, dst, tb, atten, extfft, xs, calls, got_last, channels):
+    """Replay, on a few sampled channels, every process() call the batch has seen since it was created through the
+    oracle (the compiled reference when present, else the C port) and compare what the LAST timed call wrote:
+    counts equal, max |d| <= 32 eps * max|y|, rms d <= 4 eps * rms y (the parity tolerance of tests/)."""
+    import numpy as np
+    import oracle_util as ou
+    ref = ou.best_oracle(extfft)
+    worst_max, worst_rms, ok = 0.0, 0.0, True
+    for k, ch in enumerate(channels):
+        r = ref.Resampler(src, dst, BLOCK, tb, atten)
+        y = None
+        for which in calls:
+            y = r.process(xs[which][k])
+        if y is None or len(y) != got_last.shape[1]:
+            return {"ok": False, "oracle": ref.name, "why": "count mismatch on channel %d: oracle %s, device %d"
+                    % (ch, None if y is None else len(y), got_last.shape[1])}
+        mx, rm = ou.parity_metrics(got_last[k], y)
+        worst_max, worst_rms = max(worst_max, mx), max(worst_rms, rm)
+        ok = ok and mx <= 32 * ou.EPS and rm <= 4 * ou.EPS and bool(np.all(np.isfinite(got_last[k])))
+    return {"ok": bool(ok), "oracle": ref.name, "channels": list(channels), "calls_replayed": len(calls),
+            "samples_compared": int(got_last.size), "max_err_eps": worst_max / ou.EPS, "rms_err_eps": worst_rms / ou.EPS,
+            "tolerance": "max <= 32 eps of max|y|, rms <= 4 eps of rms y, counts equal"}
 
 
 def main():
@@ -149,7 +210,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K, W = args.steps, max(args.warmup, 3)
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     config = {"workload": args.workload, "src_rate": src, "dst_rate": dst, "preset": "CDSPResampler24",
               "trans_band_pct": tb, "channels_per_gpu": n_ch, "block_frames": BLOCK, "extfft": extfft,
               "parallelism": "channels sharded over %d GPU(s), no data-path collective" % world,
@@ -163,11 +224,15 @@ def main():
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (no /root/reference at build time)"}))
             return 0
+        config["reference_sample_channels"] = r["sample_channels"]
         line = {"impl": "reference", "metric": "input Msamples/s (Mrops), fp64 %g->%g" % (src, dst),
                 "value": r["value"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
-                "ms_per_step": r["ms_per_step_equiv"], "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": r["sample_ms_per_call"], "higher_is_better": True, "scaling": "weak",
+                "ms_per_step_note": "one step of the reference arm = one process() call on each of the %d SAMPLE channels "
+                                    "(config.channels_per_gpu is the GPU arm's workload); a full %d-channel step would take %.1f ms"
+                                    % (r["sample_channels"], n_ch, r["sample_ms_per_call"] * n_ch / r["sample_channels"]),
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: r[k] for k in CPU_KEYS if k in r},
                 "e2e": {"value": r["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -206,7 +271,10 @@ def main():
     stream = torch.cuda.current_stream(dev)
     batch.set_stream(stream.cuda_stream)
 
+    call_log = []  # which input block every call since batch creation consumed (the oracle replays it)
+
     def step(i):
+        call_log.append(i & 1)
         return batch.process_ptr(xs[i & 1].data_ptr(), BLOCK, BLOCK, out.data_ptr(), cap, cap)
 
     def barrier():
@@ -233,12 +301,20 @@ def main():
     barrier()
     e0.record(stream)
     n_out_total = 0
+    step_counts = []
     for i in range(K):
-        n_out_total += step(W + i)
+        step_counts.append(step(W + i))
+    n_out_total = sum(step_counts)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = batch.kernel_launches - l0
+    # what the LAST timed call wrote, on a few sampled channels: checked against the oracle below
+    check_ch = sorted(set([0, n_ch // 3, (2 * n_ch) // 3, n_ch - 1]))
+    n_last = step_counts[-1] if step_counts else 0
+    got_last = out[check_ch, :n_last].cpu().numpy()
+    check_calls = list(call_log)
+    check_x = [x[check_ch].cpu().numpy() for x in xs]
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -305,6 +381,18 @@ def main():
                          "achieved": path_bytes_per_in * value * 1e6 / world / 1e9,
                          "frac": path_bytes_per_in * value * 1e6 / world / 1e9 / peak}}
 
+    # secondary ceiling: algorithmic flops of the path against the DFMA rate measured on this box
+    flops_in = FLOPS_PER_IN_SAMPLE.get(args.workload)
+    if flops_in is not None:
+        try:
+            pk = pkg.measure_fp64_tflops(local_rank)
+            ach = flops_in * value * 1e6 / world / 1e12
+            roofline["fp64"] = {"flops_per_in_sample": flops_in, "achieved_tflops": ach, "peak_tflops": pk,
+                                "peak_source": "measured here (r8bgpu_measure_fp64_tflops: register-resident DFMA stream)",
+                                "frac": ach / pk}
+        except Exception as e:  # the calibration is informative; never fail the bench on it
+            roofline["fp64"] = {"flops_per_in_sample": flops_in, "error": str(e)}
+
     # ---- end to end through the host-pointer C-ABI call (pinned host buffers)
     e2e = None
     if not args.no_e2e:
@@ -345,11 +433,17 @@ def main():
             e2e["float32_io"] = {"value": 1e-6 * n_ch * BLOCK * ke / (time.perf_counter() - t0), "unit": "Msamples/s",
                                  "api": "r8bgpu_batch_process_host_fmt (R8BGPU_F32 planar in/out)"}
 
+    verified = verify_against_oracle(src, dst, tb, atten, extfft, check_x, check_calls, got_last, check_ch)
+    if dist is not None:
+        t = torch.tensor([1.0 if verified["ok"] else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        verified["ok_all_ranks"] = bool(t.item() > 0.5)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_run(src, dst, tb, atten, extfft, threads, target_seconds=8.0)
         if r is not None:
-            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu = {k: r[k] for k in CPU_KEYS if k in r}
 
     if rank == 0:
         line = {"metric": "input Msamples/s (Mrops), fp64 %g->%g" % (src, dst), "value": value, "unit": "Msamples/s",
@@ -358,7 +452,8 @@ def main():
                 "vs_baseline_note": "published: 38 Mrops per core (Ooura FFT, Ryzen 3700X), README.md:111-114",
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "out_msamples_per_s": 1e-6 * world * n_ch * n_out_total / (ms * 1e-3),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "verified": bool(verified["ok"] and verified.get("ok_all_ranks", True)), "verification": verified, "roofline": roofline, "cpu_baseline": cpu,
                 "device_state_bytes": batch.device_bytes}
         print(json.dumps(line))
     if dist is not None:

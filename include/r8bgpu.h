@@ -173,6 +173,10 @@ R8BGPU_API int r8bgpu_batch_stage_kernel(const r8bgpu_batch* batch, int stage, c
 /* Bytes of device memory held by the batch (state rings + tables + staging). */
 R8BGPU_API unsigned long long r8bgpu_batch_device_bytes(const r8bgpu_batch* batch);
 
+/* Calibration for the bench's secondary (fp64) roofline: measured DFMA throughput of `device` (< 0: current) in
+ * TFLOP/s, register-resident, ~10 ms; < 0 on error.  Replaces nothing in the reference. */
+R8BGPU_API double r8bgpu_measure_fp64_tflops(int device);
+
 /* Page-locked host memory for the *_host entry points (optional but faster). */
 R8BGPU_API void* r8bgpu_host_alloc(size_t bytes);
 R8BGPU_API void r8bgpu_host_free(void* p);

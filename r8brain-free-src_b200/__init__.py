@@ -70,6 +70,7 @@ _SYMBOLS = {
     "r8bgpu_batch_stage_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
     "r8bgpu_batch_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "r8bgpu_batch_stage_time_ms": (C.c_double, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]),
+    "r8bgpu_measure_fp64_tflops": (C.c_double, [C.c_int]),
     "r8bgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
     "r8bgpu_host_free": (None, [C.c_void_p]),
 }
@@ -118,6 +119,14 @@ def _err():
 
 def device_count():
     return lib().r8bgpu_device_count()
+
+
+def measure_fp64_tflops(device=-1):
+    """Measured DFMA ceiling of the device (bench.py's secondary roofline)."""
+    v = lib().r8bgpu_measure_fp64_tflops(int(device))
+    if v < 0:
+        raise R8bGpuError(_err())
+    return v
 
 
 class Plan:

@@ -155,7 +155,7 @@ struct r8bgpu_batch {
     std::vector<cudaEvent_t> ev_h2d, ev_k;
     unsigned long long* prof = nullptr; // R8BGPU_PROFILE: phase cycle counters of the fused kernel
     int n_sm = 0;     // SMs of the device (grid of the persistent v2 fused kernel)
-    int f2_flags = 3; // v2 fused kernel: bit 0 ping-pong token, bit 1 bulk-copied input tiles
+    int f2_flags = 7; // v2 fused kernel: bit 0 ping-pong token, bit 1 bulk-copied input tiles, bit 2 interpolation on the fp64 tensor path
     unsigned long long prof_ctas = 0;
 
     ~r8bgpu_batch()
@@ -456,7 +456,9 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
             if (s.kind == ST_FRAC_WHOLE) {
                 // per output phase r: floor(r*InStep/OutStep) and the bank row (r*InStep) % OutStep; grouped bank for
                 // the fused kernels: IR consecutive phases share one y window
-                const GroupBank B = build_group_bank(s, choose_group_ir(s));
+                // (the tensor-path interpolation of the v2 kernel works on groups of exactly 8 phases)
+                const bool want_f2 = d.fused_into_prev && i > 0 && !getenv("R8BGPU_FUSED_V1");
+                const GroupBank B = build_group_bank(s, (want_f2 && (b->f2_flags & 4)) ? 8 : choose_group_ir(s));
                 const size_t tb = B.off.size() * sizeof(int);
                 if (!cuda_ok(cudaMalloc(&d.phase_off, tb), "cudaMalloc(phase)")) return nullptr;
                 if (!cuda_ok(cudaMalloc(&d.phase_row, tb), "cudaMalloc(phase)")) return nullptr;
@@ -473,8 +475,7 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 b->dev_bytes += B.gb.size() * sizeof(double);
                 d.bank_in_smem = (fused_smem_bytes(d.gbank_smem_len) <= 220 * 1024) ? 1 : 0;
                 // the persistent two-pipeline kernel needs the call's whole bank in shared memory
-                if (d.fused_into_prev && i > 0 && fused2_smem_bytes(d.gbank_smem_len, false) <= kFused2SmemMax &&
-                    (s.out_step + d.ir - 1) / d.ir <= 192 && !getenv("R8BGPU_FUSED_V1"))
+                if (want_f2 && fused2_smem_bytes(d.gbank_smem_len, false) <= kFused2SmemMax && (s.out_step + d.ir - 1) / d.ir <= 192)
                     b->dev[i - 1].f2_ok = true;
             }
         }
@@ -806,8 +807,9 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.n_ch = nch;
                 p.flags = b->f2_flags;
                 p.tw_tab = d.tw_tab;
-                p.stage_off = (p.ir == 8 && fused2_smem_bytes(p.gbank_smem_len, true) <= kFused2SmemMax && !getenv("R8BGPU_NO_STAGE"))
-                                  ? fused2_stage_off(p.gbank_smem_len) : 0;
+                if (p.ir != 8) p.flags &= ~4;
+                p.stage_off = (p.ir == 8 && !(p.flags & 4) && fused2_smem_bytes(p.gbank_smem_len, true) <= kFused2SmemMax &&
+                               !getenv("R8BGPU_NO_STAGE")) ? fused2_stage_off(p.gbank_smem_len) : 0;
                 p.glog = fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
                 launch_up2_frac2(p, src, dst, b->n_sm, st);
             } else {
@@ -1204,6 +1206,20 @@ int r8bgpu_batch_process_fmt(r8bgpu_batch* b, const r8bgpu_buffer* d_in, int l, 
     }
     if (!cuda_ok(cudaGetLastError(), "batch_process_fmt: kernel launch")) return -1;
     return n;
+}
+
+double r8bgpu_measure_fp64_tflops(int device)
+{
+    int dev = device;
+    if (dev < 0 && !cuda_ok(cudaGetDevice(&dev), "measure_fp64")) return -1.0;
+    DeviceGuard guard(dev);
+    if (!guard.ok) {
+        set_err("measure_fp64: cannot select device");
+        return -1.0;
+    }
+    const double tf = measure_dfma_tflops();
+    if (tf < 0.0) cuda_ok(cudaGetLastError(), "measure_fp64");
+    return tf;
 }
 
 void* r8bgpu_host_alloc(size_t bytes)

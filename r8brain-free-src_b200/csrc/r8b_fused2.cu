@@ -124,8 +124,15 @@ __device__ __forceinline__ void interp_store_staged(const FusedParams& p, const 
 
 } // namespace
 
+// D = A(8x4, row) * B(4x8, col) + D on the fp64 tensor path (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // flags: bit 0 = ping-pong token around the interpolation, bit 1 = bulk-copy input tiles
-template <int IRV, bool PADV, int GLOG>
+// TC: interpolation as 8x8x4 fp64 matrix products (IRV == 8; GLOG unused)
+template <int IRV, bool PADV, int GLOG, bool TC>
 __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ FusedParams p, const __grid_constant__ SrcView src,
                                                       const __grid_constant__ DstView dst)
 {
@@ -242,7 +249,29 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
         {
             const double* yb = reinterpret_cast<const double*>(buf);
             const int* si = s_i[h];
-            if (si[0] > 0) {
+            if constexpr (TC) {
+                const int n_mu = si[0] > 0 ? mma_units(p, si[1]) : 0, ksteps = p.smaxp >> 2;
+                for (int unit = wh; unit < n_mu; unit += HT / 32) {
+                    int yo[MBU];
+#pragma unroll
+                    for (int i = 0; i < MBU; i++) yo[i] = mma_a_index(p, s_goff, si, unit, i, lane);
+                    const double* gb = sbank + mma_b_index(p, unit, lane);
+                    double acc[MBU][2];
+#pragma unroll
+                    for (int i = 0; i < MBU; i++) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll 4
+                    for (int ks = 0; ks < ksteps; ks++) {
+                        const double b = gb[ks * 32];
+#pragma unroll
+                        for (int i = 0; i < MBU; i++) {
+                            const int yi = yo[i] + 4 * ks;
+                            dmma884(acc[i][0], acc[i][1], PADV ? yb[ylay(yi, p.ysh)] : yb[yi], b);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < MBU; i++) mma_store(p, dst, t.ch, si, s_o[h], unit, i, lane, acc[i][0], acc[i][1]);
+                }
+            } else if (si[0] > 0) {
                 const int n_tasks = TaskGeom<IRV, GLOG>::n_tasks(p, si[1]);
                 double* const stg = p.stage_off > 0 ? reinterpret_cast<double*>(smem) + p.stage_off + (tid >> 5) * 256 : nullptr;
                 for (int task = wh; task < n_tasks; task += HT / 32) {
@@ -281,11 +310,11 @@ int fused2_smem_bytes(int bank_doubles, bool staged)
 }
 int fused2_stage_off(int bank_doubles) { return 2 * (2 * FPL + 512) + ((bank_doubles + 1) & ~1); }
 
-template <int IRV, bool PADV, int GLOG>
+template <int IRV, bool PADV, int GLOG, bool TC = false>
 static void launch_inst2(const FusedParams& p, const SrcView& src, const DstView& dst, int grid, int smem, cudaStream_t st)
 {
-    ensure_dyn_smem<k_up2_frac2<IRV, PADV, GLOG>>(227 * 1024);
-    k_up2_frac2<IRV, PADV, GLOG><<<(unsigned) grid, NT2, smem, st>>>(p, src, dst);
+    ensure_dyn_smem<k_up2_frac2<IRV, PADV, GLOG, TC>>(227 * 1024);
+    k_up2_frac2<IRV, PADV, GLOG, TC><<<(unsigned) grid, NT2, smem, st>>>(p, src, dst);
 }
 
 // p.n_ch, p.n_tiles, p.span ... describe the call; n_sm = SMs of the device (persistent grid).
@@ -300,7 +329,10 @@ void launch_up2_frac2(const FusedParams& p, const SrcView& src, const DstView& d
 #define R8B_F2_CASE(IRV, GL)                                                              \
     if (pad) launch_inst2<IRV, true, GL>(p, src, dst, grid, smem, st);                    \
     else launch_inst2<IRV, false, GL>(p, src, dst, grid, smem, st);
-    if (p.ir == 10) {
+    if (p.ir == 8 && (p.flags & 4)) {
+        if (pad) launch_inst2<8, true, 0, true>(p, src, dst, grid, smem, st);
+        else launch_inst2<8, false, 0, true>(p, src, dst, grid, smem, st);
+    } else if (p.ir == 10) {
         if (p.glog == 2) { R8B_F2_CASE(10, 2) } else if (p.glog == 1) { R8B_F2_CASE(10, 1) } else { R8B_F2_CASE(10, 0) }
     } else {
         if (p.glog == 2) { R8B_F2_CASE(8, 2) } else if (p.glog == 1) { R8B_F2_CASE(8, 1) } else { R8B_F2_CASE(8, 0) }

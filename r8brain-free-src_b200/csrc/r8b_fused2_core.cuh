@@ -275,5 +275,71 @@ R8B_HD void interp_store_direct(const FusedParams& p, const DstView& dst, int ch
     }
 }
 
+// ---- interpolation on the fp64 tensor path (mma.sync m8n8k4 = SASS DMMA) ---------------------------------------
+// One phase group is a small GEMM: out[c][r] = sum_s Y[c][s] * Bp[s][r], with Y[c][s] = y[c*in_step + o0 + s] a
+// strided (Hankel) view of the tile's 2x-rate stream, Bp the group's pre-shifted zero-padded filters [smaxp][8],
+// c the stepping cycle, r the phase within the group.  m8n8k4 fragments: A (8x4): lane holds A[lane/4][lane%4];
+// B (4x8): lane holds B[lane%4][lane/4]; C (8x8): lane holds C[lane/4][2*(lane%4) + {0,1}] -- i.e. a lane ends up
+// with two CONSECUTIVE outputs of one stepping cycle and four lanes hold one 64-byte output row, so results go
+// straight from the accumulators to global memory with no transposition.  Against the register-tiled FMA loop the
+// shared-memory traffic per multiply-add halves (each loaded Y value feeds 8 products, each Bp value MBU*8) and
+// 256 multiply-adds issue as one instruction.  A work unit = one group x MBU blocks of 8 stepping cycles.
+constexpr int MBU = 3;
+
+R8B_HD int mma_units(const FusedParams& p, int c_cnt)
+{
+    const int n_groups = (p.out_step + 7) / 8, n_mb = c_cnt / 8 + 1;
+    return n_groups * ((n_mb + MBU - 1) / MBU);
+}
+
+// y index (before the padded-layout map) of the lane's A element of block i at K-step 0
+R8B_HD int mma_a_index(const FusedParams& p, const int* __restrict__ s_goff, const int* __restrict__ s_i, int unit, int i, int lane)
+{
+    const int n_groups = (p.out_step + 7) / 8;
+    const int g = unit % n_groups, chunk = unit / n_groups;
+    int c = (chunk * MBU + i) * 8 + (lane >> 2);
+    if (c > s_i[1]) c = s_i[1];             // rows past the last cycle compute something valid and never store
+    int li = c * p.in_step + s_goff[g] + s_i[3];
+    if (li < 0) li = 0;
+    if (li > 2 * FM - p.smaxp) li = 2 * FM - p.smaxp;
+    return li + (lane & 3);
+}
+
+// offset of the lane's B element at K-step 0 inside the call's bank (K-step ks adds 32*ks)
+R8B_HD int mma_b_index(const FusedParams& p, int unit, int lane)
+{
+    const int n_groups = (p.out_step + 7) / 8;
+    return (unit % n_groups) * p.smaxp * 8 + (lane & 3) * 8 + (lane >> 2);
+}
+
+// the lane's two results of block i: outputs (cycle, phases 2*(lane%4), +1) of the group
+R8B_HD void mma_store(const FusedParams& p, const DstView& dst, int ch, const int* __restrict__ s_i, double* s_o, int unit, int i,
+                      int lane, double c0, double c1)
+{
+    const int n_groups = (p.out_step + 7) / 8;
+    const int g = unit % n_groups, chunk = unit / n_groups;
+    const int c = (chunk * MBU + i) * 8 + (lane >> 2);
+    if (c > s_i[1]) return;
+    const int n_j = s_i[0], rr = p.delta + g * 8 + 2 * (lane & 3);
+    const int j = c * p.out_step + rr + s_i[2];
+    const bool in0 = (p.wrap || rr < p.out_step) && j >= 0 && j < n_j;
+    const bool in1 = (p.wrap || rr + 1 < p.out_step) && j + 1 >= 0 && j + 1 < n_j;
+    if (dst.mask == -1) {
+        double* o = s_o + j;
+        if (in0 && in1 && (reinterpret_cast<unsigned long long>(o) & 15) == 0) {
+            *reinterpret_cast<double2*>(o) = make_double2(c0, c1);
+        } else {
+            if (in0) o[0] = c0;
+            if (in1) o[1] = c1;
+        }
+    } else { // ring destination (another stage follows): s_o is the ring slot of the tile's first output
+        double* const rb = dst.ptr + (long long) ch * dst.stride;
+        const long long i0 = (s_o - rb) + (long long) j;
+        if (in0) rb[i0 & dst.mask] = c0;
+        if (in1) rb[(i0 + 1) & dst.mask] = c1;
+    }
+}
+
 } // namespace f2
+
 } // namespace r8bgpu

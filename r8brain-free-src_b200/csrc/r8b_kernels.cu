@@ -608,4 +608,49 @@ void launch_hbup_cascade(const HbCascadeParams& p, int smem_bytes, const SrcView
     k_hbup_cascade<<<grid, HB_NT, smem_bytes, st>>>(p, src, dst);
 }
 
+namespace {
+__global__ void __launch_bounds__(1024) k_dfma_peak(double* out, int iters, double a, double b)
+{
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i];
+    if (s == 12345.678) out[0] = s; // never true: keeps the chains alive without a store stream
+}
+} // namespace
+
+double measure_dfma_tflops()
+{
+    int dev = 0, n_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1.0;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double)) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 8192, nt = 1024;
+    double best = -1.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, 0);
+        k_dfma_peak<<<n_sm, nt>>>(out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, 0);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 16.0 * iters * (double) nt * n_sm / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf; // first launch is the warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
+
 } // namespace r8bgpu

@@ -160,6 +160,10 @@ int fused_stage_doubles();
 int fused_fixed_doubles();
 int fused_poly_queue_bytes();
 void launch_up2_frac(const FusedParams& p, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st);
+// Calibration: best-of-3 TFLOP/s of a register-resident DFMA stream (16 independent chains per thread, 32 warps per
+// SM) on the current device -- the fp64 ceiling the bench reports next to the HBM roofline.  < 0 on error.
+double measure_dfma_tflops();
+
 constexpr int kFused2SmemMax = 227 * 1024 - 1024; // dynamic part; the kernel's static shared memory is < 1 KB
 int fused2_smem_bytes(int bank_doubles, bool staged);
 int fused2_stage_off(int bank_doubles);

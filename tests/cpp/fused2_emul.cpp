@@ -28,7 +28,40 @@ struct Emul {
     std::vector<double> ring; // the whole past of the input stream (power-of-two ring, zero before the start)
     long long ring_mask = 0;
     int glog_force = -1;
+    bool tc = false; // interpolation through the m8n8k4 formulation (glog_force == 8)
 };
+
+// the tensor-path interpolation: one m8n8k4 product per (block of 8 cycles, K-step), emulated on whole "warps" with the
+// fragment layouts of mma.sync (A: lane = 4*row + k, B: lane = 4*n + k, C: lane = 4*row + col/2)
+template <bool PADV>
+void interp_tc(const FusedParams& p, const DstView& dst, const Tile& t, const double* yb, const double* sbank, const int* s_goff,
+               const int* s_i, double* s_o)
+{
+    const int n_mu = mma_units(p, s_i[1]), ksteps = p.smaxp >> 2;
+    for (int unit = 0; unit < n_mu; unit++) {
+        double acc[MBU][32][2] = {};
+        for (int ks = 0; ks < ksteps; ks++) {
+            double b[32];
+            for (int lane = 0; lane < 32; lane++) b[lane] = sbank[mma_b_index(p, unit, lane) + ks * 32];
+            for (int i = 0; i < MBU; i++) {
+                double a[32];
+                for (int lane = 0; lane < 32; lane++) {
+                    const int yi = mma_a_index(p, s_goff, s_i, unit, i, lane) + 4 * ks;
+                    a[lane] = PADV ? yb[ylay(yi, p.ysh)] : yb[yi];
+                }
+                for (int lane = 0; lane < 32; lane++) {
+                    const int row = lane >> 2, col = 2 * (lane & 3);
+                    for (int k = 0; k < 4; k++) {
+                        acc[i][lane][0] = fma(a[4 * row + k], b[4 * col + k], acc[i][lane][0]);
+                        acc[i][lane][1] = fma(a[4 * row + k], b[4 * (col + 1) + k], acc[i][lane][1]);
+                    }
+                }
+            }
+        }
+        for (int i = 0; i < MBU; i++)
+            for (int lane = 0; lane < 32; lane++) mma_store(p, dst, t.ch, s_i, s_o, unit, i, lane, acc[i][lane][0], acc[i][lane][1]);
+    }
+}
 
 template <int IR, bool PADV, int GLOG>
 void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, const Emul& E)
@@ -94,7 +127,9 @@ void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, con
                 y_store<PADV>(buf.data(), a, ht, t.w, p.ysh);
             }
         }
-        if (s_i[0] > 0) {
+        if (s_i[0] > 0 && E.tc) {
+            if constexpr (IR == 8) interp_tc<PADV>(p, dst, t, reinterpret_cast<const double*>(buf.data()), sbank.data(), s_goff.data(), s_i, s_o);
+        } else if (s_i[0] > 0) {
             const double* yb = reinterpret_cast<const double*>(buf.data());
             const int n_tasks = TaskGeom<IR, GLOG>::n_tasks(p, s_i[1]);
             for (int task = 0; task < n_tasks; task++)
@@ -139,12 +174,13 @@ void* f2emul_create(double src, double dst, int max_in_len, double tb, double at
         return nullptr;
     }
     E->sched.init(&E->plan);
-    E->B = build_group_bank(E->plan.stages[1], choose_group_ir(E->plan.stages[1]));
+    E->tc = glog_force == 8;
+    E->B = build_group_bank(E->plan.stages[1], E->tc ? 8 : choose_group_ir(E->plan.stages[1]));
     build_spectrum(E->plan.stages[0], 12, E->spec, E->tw, nullptr);
     E->tw_tab = build_tw_tab(E->tw);
     E->ring.assign((size_t) 1 << 22, 0.0);
     E->ring_mask = ((long long) 1 << 22) - 1;
-    E->glog_force = glog_force;
+    E->glog_force = E->tc ? -1 : glog_force;
     return E;
 }
 
@@ -175,7 +211,7 @@ int f2emul_process(void* h, const double* x, int l, double* out, int out_cap)
         p.ir = E.B.ir;
         p.gbank_smem_len = E.B.n_groups * E.B.smaxp * E.B.ir;
         p.n_ch = 1;
-        p.glog = E.glog_force >= 0 ? E.glog_force : fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
+        p.glog = E.tc ? 0 : E.glog_force >= 0 ? E.glog_force : fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
         SrcView src;
         src.ring = E.ring.data();
         src.ring_stride = (long long) E.ring.size();

@@ -75,6 +75,14 @@ def test_cfg2_chain_all_lane_splits(emul, glog):
     _run(emul, 44100.0, 96000.0, 8192, [8192, 8192, 8192], glog=glog)
 
 
+@pytest.mark.parametrize("src,dst,lens", [(44100.0, 96000.0, [8192, 8192, 3, 0, 4097, 8191]),
+                                          (48000.0, 44100.0, [8191, 8191, 4000]),       # padded y layout, 19 groups
+                                          (44100.0, 48000.0, [4096] * 3)])
+def test_tensor_path_interpolation(emul, src, dst, lens):
+    """glog = 8 selects the m8n8k4 formulation (fragment index functions of r8b_fused2_core.cuh)."""
+    _run(emul, src, dst, max(lens), lens, glog=8)
+
+
 def test_ragged_blocks_history_ring_and_misaligned_rows(emul):
     # odd lengths shift the block base parity (plain-load path), tiny and empty blocks reach into the history ring
     _run(emul, 44100.0, 96000.0, 8192, [1, 0, 4097, 777, 8192, 3, 8191, 5000])
