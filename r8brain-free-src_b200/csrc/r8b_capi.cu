@@ -115,6 +115,7 @@ struct StageDev {
     int casc_len = 0; // >= 2 on the first stage of a run of HBUP stages executed by k_hbup_cascade
     // v2 fused kernel (r8b_fused2.cu): [q][r] twiddle tables for the bulk copy; on the BLOCKCONV stage
     double2* tw_tab = nullptr;
+    double2* c_tab = nullptr;   // v2 fused kernel: phase C operands in thread order
     bool f2_ok = false;
     FusedGeom fgeom;
 };
@@ -155,7 +156,7 @@ struct r8bgpu_batch {
     std::vector<cudaEvent_t> ev_h2d, ev_k;
     unsigned long long* prof = nullptr; // R8BGPU_PROFILE: phase cycle counters of the fused kernel
     int n_sm = 0;     // SMs of the device (grid of the persistent v2 fused kernel)
-    int f2_flags = 7; // v2 fused kernel: bit 0 ping-pong token, bit 1 bulk-copied input tiles, bit 2 interpolation on the fp64 tensor path
+    int f2_flags = 6; // v2 fused kernel: bit 0 ping-pong token, bit 1 bulk-copied input tiles, bit 2 interpolation on the fp64 tensor path
     unsigned long long prof_ctas = 0;
 
     ~r8bgpu_batch()
@@ -181,6 +182,7 @@ struct r8bgpu_batch {
             cudaFree(d.spec);
             cudaFree(d.tw);
             cudaFree(d.tw_tab);
+            cudaFree(d.c_tab);
             cudaFree(d.bank);
             cudaFree(d.ring);
             cudaFree(d.phase_off);
@@ -437,6 +439,9 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 const std::vector<double2> tt = build_tw_tab(tw);
                 if (!cuda_ok(cudaMalloc(&d.tw_tab, tt.size() * sizeof(double2)), "cudaMalloc(tw_tab)")) return nullptr;
                 if (!cuda_ok(cudaMemcpy(d.tw_tab, tt.data(), tt.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy tw_tab")) return nullptr;
+                const std::vector<double2> ctb = build_c_tab(spec, tw);
+                if (!cuda_ok(cudaMalloc(&d.c_tab, ctb.size() * sizeof(double2)), "cudaMalloc(c_tab)")) return nullptr;
+                if (!cuda_ok(cudaMemcpy(d.c_tab, ctb.data(), ctb.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy c_tab")) return nullptr;
             }
         } else if (s.kind == ST_FRAC_WHOLE || s.kind == ST_FRAC_POLY) {
             const size_t nb = s.bank.table.size() * sizeof(double);
@@ -807,6 +812,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.n_ch = nch;
                 p.flags = b->f2_flags;
                 p.tw_tab = d.tw_tab;
+                p.c_tab = d.c_tab;
                 if (p.ir != 8) p.flags &= ~4;
                 p.stage_off = (p.ir == 8 && !(p.flags & 4) && fused2_smem_bytes(p.gbank_smem_len, true) <= kFused2SmemMax &&
                                !getenv("R8BGPU_NO_STAGE")) ? fused2_stage_off(p.gbank_smem_len) : 0;

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
             if (ht == 0) ze = buf[fft_pad(slot_of<FN>(FN / 2))];
             bar_half(h);
 #pragma unroll
-            for (int i = 0; i < 4; i++) c_pair(p, buf, c_freq(ht, i), z1[i], z2[i]);
+            for (int i = 0; i < 4; i++) c_pair_tab(p, buf, ht, i, z1[i], z2[i]);
             if (ht == 0) c_pair(p, buf, FN / 2, ze, ze);
         }
         bar_half(h);
@@ -250,12 +250,18 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
             const double* yb = reinterpret_cast<const double*>(buf);
             const int* si = s_i[h];
             if constexpr (TC) {
-                const int n_mu = si[0] > 0 ? mma_units(p, si[1]) : 0, ksteps = p.smaxp >> 2;
-                for (int unit = wh; unit < n_mu; unit += HT / 32) {
+                MmaTile mt;
+                mt.load(si);
+                const int n_mu = mt.n_j > 0 ? mma_units(p, mt.c_cnt) : 0, ksteps = p.smaxp >> 2;
+                double* const so = s_o[h];
+                MmaUnit mu;
+                mu.set(wh, n_groups);
+                for (int unit = wh; unit < n_mu; unit += HT / 32, mu.advance(HT / 32, n_groups)) {
+                    const int goff = s_goff[mu.g];
                     int yo[MBU];
 #pragma unroll
-                    for (int i = 0; i < MBU; i++) yo[i] = mma_a_index(p, s_goff, si, unit, i, lane);
-                    const double* gb = sbank + mma_b_index(p, unit, lane);
+                    for (int i = 0; i < MBU; i++) yo[i] = mma_a_index(p, mt, mu, goff, i, lane);
+                    const double* gb = sbank + mma_b_index(p, mu, lane);
                     double acc[MBU][2];
 #pragma unroll
                     for (int i = 0; i < MBU; i++) acc[i][0] = acc[i][1] = 0.0;
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < MBU; i++) mma_store(p, dst, t.ch, si, s_o[h], unit, i, lane, acc[i][0], acc[i][1]);
+                    for (int i = 0; i < MBU; i++) mma_store(p, dst, t.ch, mt, so, mu, i, lane, acc[i][0], acc[i][1]);
                 }
             } else if (si[0] > 0) {
                 const int n_tasks = TaskGeom<IRV, GLOG>::n_tasks(p, si[1]);

@@ -109,18 +109,34 @@ R8B_HD void c_load(const double2* __restrict__ buf, int ht, double2 (&z1)[4], do
 //   2X[k] = A' + W^k B',  2X[k+N] = A' - W^k B',  X[N-k] = conj X[k+N],  X[M-k] = conj X[k]
 // (the factor 2 lives in G).  k = 0 and k = N/2 pair with themselves; their four stores collapse to two
 // locations written with equal values.
-R8B_HD void c_pair(const FusedParams& p, double2* __restrict__ buf, int k, double2 z1, double2 z2)
+R8B_HD void c_pair_ops(double2* __restrict__ buf, int k, double2 z1, double2 z2, double2 w, double2 g0, double2 g1, double2 g2,
+                       double2 g3)
 {
     const double2 a = make_double2(z1.x + z2.x, z1.y - z2.y);
     const double2 b = make_double2(z1.y + z2.y, z2.x - z1.x);
-    const double2 wb = cmul<+1>(b, R8B_LDG(&p.tw[k]));
+    const double2 wb = cmul<+1>(b, w);
     const double2 x0 = make_double2(a.x + wb.x, a.y + wb.y);
     const double2 x1 = make_double2(a.x - wb.x, a.y - wb.y);
     const int s0 = slot_of<FM>(k), s1 = slot_of<FM>(k + FN), s2 = slot_of<FM>(FN - k), s3 = slot_of<FM>((FM - k) & (FM - 1));
-    buf[fft_pad(s0)] = cmul<+1>(x0, R8B_LDG(&p.spec[s0]));
-    buf[fft_pad(s1)] = cmul<+1>(x1, R8B_LDG(&p.spec[s1]));
-    buf[fft_pad(s2)] = cmul<+1>(make_double2(x1.x, -x1.y), R8B_LDG(&p.spec[s2]));
-    buf[fft_pad(s3)] = cmul<+1>(make_double2(x0.x, -x0.y), R8B_LDG(&p.spec[s3]));
+    buf[fft_pad(s0)] = cmul<+1>(x0, g0);
+    buf[fft_pad(s1)] = cmul<+1>(x1, g1);
+    buf[fft_pad(s2)] = cmul<+1>(make_double2(x1.x, -x1.y), g2);
+    buf[fft_pad(s3)] = cmul<+1>(make_double2(x0.x, -x0.y), g3);
+}
+
+// operands from the natural tables (spectrum in slot order, W_M^k): scattered reads, used for the one extra pair k = N/2
+R8B_HD void c_pair(const FusedParams& p, double2* __restrict__ buf, int k, double2 z1, double2 z2)
+{
+    c_pair_ops(buf, k, z1, z2, R8B_LDG(&p.tw[k]), R8B_LDG(&p.spec[slot_of<FM>(k)]), R8B_LDG(&p.spec[slot_of<FM>(k + FN)]),
+               R8B_LDG(&p.spec[slot_of<FM>(FN - k)]), R8B_LDG(&p.spec[slot_of<FM>((FM - k) & (FM - 1))]));
+}
+
+// operands from the thread-ordered table p.c_tab ([u][item][ht]: a warp's 32 loads of one item are 512 contiguous bytes;
+// the natural tables put a warp's 32 operands on 32 different cache lines)
+R8B_HD void c_pair_tab(const FusedParams& p, double2* __restrict__ buf, int ht, int u, double2 z1, double2 z2)
+{
+    const double2* __restrict__ ct = p.c_tab + (u * 5) * HT + ht;
+    c_pair_ops(buf, c_freq(ht, u), z1, z2, R8B_LDG(ct), R8B_LDG(ct + HT), R8B_LDG(ct + 2 * HT), R8B_LDG(ct + 3 * HT), R8B_LDG(ct + 4 * HT));
 }
 
 // inverse, last pass (NCUR = M, D = 256): loads + butterfly; the results leave through y_store()
@@ -284,46 +300,78 @@ R8B_HD void interp_store_direct(const FusedParams& p, const DstView& dst, int ch
 // straight from the accumulators to global memory with no transposition.  Against the register-tiled FMA loop the
 // shared-memory traffic per multiply-add halves (each loaded Y value feeds 8 products, each Bp value MBU*8) and
 // 256 multiply-adds issue as one instruction.  A work unit = one group x MBU blocks of 8 stepping cycles.
+//
+// Which stepping cycle a fragment row stands for is free.  An LDS.64 is served one half-warp at a time, and the
+// four rows of a half-warp (4 consecutive doubles each) are conflict-free exactly when their starts are 4 or 12
+// doubles apart mod 16.  Windows of cycles kappa apart start kappa*in_step doubles apart, and for every odd in_step
+// kappa = 4 gives 4*in_step = 4 or 12 (mod 16): so the rows of a half-warp take cycles 4 apart, and two blocks
+// interleave to cover 16 consecutive cycles:  cycle(block, row) = 16*(block/2) + 4*(row%4) + 2*(block%2) + row/4.
+// (Even in_step: the padded y layout makes the stride odd on average; the same map is used.)
 constexpr int MBU = 3;
+
+R8B_HD int mma_cycle(int block, int row) { return 16 * (block >> 1) + 4 * (row & 3) + 2 * (block & 1) + (row >> 2); }
 
 R8B_HD int mma_units(const FusedParams& p, int c_cnt)
 {
-    const int n_groups = (p.out_step + 7) / 8, n_mb = c_cnt / 8 + 1;
+    const int n_groups = (p.out_step + 7) / 8, n_mb = 2 * (c_cnt / 16 + 1);
     return n_groups * ((n_mb + MBU - 1) / MBU);
 }
 
+// A work unit's place in the tile: its phase group and which MBU blocks of cycles it covers.  Units are dealt to the
+// warps of a half round-robin, so the pair (group, chunk) advances without a division.
+struct MmaUnit {
+    int g, chunk;
+    R8B_HD void set(int unit, int n_groups)
+    {
+        chunk = unit / n_groups;
+        g = unit - chunk * n_groups;
+    }
+    R8B_HD void advance(int by, int n_groups)
+    {
+        g += by;
+        while (g >= n_groups) {
+            g -= n_groups;
+            chunk++;
+        }
+    }
+};
+
+// Tile-level values every unit needs (read once per tile from the bookkeeping interp_prepare() left in shared memory)
+struct MmaTile {
+    int n_j, c_cnt, jshift, wbase;
+    R8B_HD void load(const int* __restrict__ s_i)
+    {
+        n_j = s_i[0];
+        c_cnt = s_i[1];
+        jshift = s_i[2];
+        wbase = s_i[3];
+    }
+};
+
 // y index (before the padded-layout map) of the lane's A element of block i at K-step 0
-R8B_HD int mma_a_index(const FusedParams& p, const int* __restrict__ s_goff, const int* __restrict__ s_i, int unit, int i, int lane)
+R8B_HD int mma_a_index(const FusedParams& p, const MmaTile& mt, const MmaUnit& u, int goff, int i, int lane)
 {
-    const int n_groups = (p.out_step + 7) / 8;
-    const int g = unit % n_groups, chunk = unit / n_groups;
-    int c = (chunk * MBU + i) * 8 + (lane >> 2);
-    if (c > s_i[1]) c = s_i[1];             // rows past the last cycle compute something valid and never store
-    int li = c * p.in_step + s_goff[g] + s_i[3];
+    int c = mma_cycle(u.chunk * MBU + i, lane >> 2);
+    if (c > mt.c_cnt) c = mt.c_cnt;          // rows past the last cycle compute something valid and never store
+    int li = c * p.in_step + goff + mt.wbase;
     if (li < 0) li = 0;
     if (li > 2 * FM - p.smaxp) li = 2 * FM - p.smaxp;
     return li + (lane & 3);
 }
 
 // offset of the lane's B element at K-step 0 inside the call's bank (K-step ks adds 32*ks)
-R8B_HD int mma_b_index(const FusedParams& p, int unit, int lane)
-{
-    const int n_groups = (p.out_step + 7) / 8;
-    return (unit % n_groups) * p.smaxp * 8 + (lane & 3) * 8 + (lane >> 2);
-}
+R8B_HD int mma_b_index(const FusedParams& p, const MmaUnit& u, int lane) { return u.g * p.smaxp * 8 + (lane & 3) * 8 + (lane >> 2); }
 
 // the lane's two results of block i: outputs (cycle, phases 2*(lane%4), +1) of the group
-R8B_HD void mma_store(const FusedParams& p, const DstView& dst, int ch, const int* __restrict__ s_i, double* s_o, int unit, int i,
-                      int lane, double c0, double c1)
+R8B_HD void mma_store(const FusedParams& p, const DstView& dst, int ch, const MmaTile& mt, double* s_o, const MmaUnit& u, int i, int lane,
+                      double c0, double c1)
 {
-    const int n_groups = (p.out_step + 7) / 8;
-    const int g = unit % n_groups, chunk = unit / n_groups;
-    const int c = (chunk * MBU + i) * 8 + (lane >> 2);
-    if (c > s_i[1]) return;
-    const int n_j = s_i[0], rr = p.delta + g * 8 + 2 * (lane & 3);
-    const int j = c * p.out_step + rr + s_i[2];
-    const bool in0 = (p.wrap || rr < p.out_step) && j >= 0 && j < n_j;
-    const bool in1 = (p.wrap || rr + 1 < p.out_step) && j + 1 >= 0 && j + 1 < n_j;
+    const int c = mma_cycle(u.chunk * MBU + i, lane >> 2);
+    if (c > mt.c_cnt) return;
+    const int rr = p.delta + u.g * 8 + 2 * (lane & 3);
+    const int j = c * p.out_step + rr + mt.jshift;
+    const bool in0 = (p.wrap || rr < p.out_step) && j >= 0 && j < mt.n_j;
+    const bool in1 = (p.wrap || rr + 1 < p.out_step) && j + 1 >= 0 && j + 1 < mt.n_j;
     if (dst.mask == -1) {
         double* o = s_o + j;
         if (in0 && in1 && (reinterpret_cast<unsigned long long>(o) & 15) == 0) {

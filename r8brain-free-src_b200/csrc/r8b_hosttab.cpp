@@ -1,6 +1,8 @@
 // r8b_hosttab.cpp -- see r8b_hosttab.h.
 #include "r8b_hosttab.h"
 
+#include "r8b_fused2_core.cuh"
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -86,6 +88,23 @@ std::vector<double2> build_tw_tab(const std::vector<double2>& tw)
             tt[(size_t) (256 + q * 16 + r)] = tw[(size_t) (r * q)];    // W_4096^(r q)
         }
     return tt;
+}
+
+std::vector<double2> build_c_tab(const std::vector<double2>& spec, const std::vector<double2>& tw)
+{
+    using namespace f2;
+    std::vector<double2> ct((size_t) 4 * 5 * HT);
+    for (int u = 0; u < 4; u++)
+        for (int ht = 0; ht < HT; ht++) {
+            const int k = c_freq(ht, u);
+            double2* e = &ct[(size_t) (u * 5) * HT + ht];
+            e[0] = tw[(size_t) k];
+            e[HT] = spec[(size_t) slot_of<FM>(k)];
+            e[2 * HT] = spec[(size_t) slot_of<FM>(k + FN)];
+            e[3 * HT] = spec[(size_t) slot_of<FM>(FN - k)];
+            e[4 * HT] = spec[(size_t) slot_of<FM>((FM - k) & (FM - 1))];
+        }
+    return ct;
 }
 
 FusedGeom fused_geometry(const StageDesc& s, const StageDesc& f)

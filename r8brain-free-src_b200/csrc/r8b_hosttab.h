@@ -19,6 +19,8 @@ void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec
 
 // [q][r] twiddle tables of the fused kernels: 256 entries W_256^(r q), then 256 entries W_4096^(r q)
 std::vector<double2> build_tw_tab(const std::vector<double2>& tw4096);
+// phase C operands of the v2 fused kernel in thread order (FusedParams::c_tab)
+std::vector<double2> build_c_tab(const std::vector<double2>& spec_slots4096, const std::vector<double2>& tw4096);
 
 // "2x BlockConvolver -> FracInterpolator" pair: margins and span of the M = 4096 tiles
 struct FusedGeom {

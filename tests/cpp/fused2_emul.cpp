@@ -24,7 +24,7 @@ struct Emul {
     std::vector<StageCall> calls;
     FusedGeom fg;
     GroupBank B;
-    std::vector<double2> spec, tw, tw_tab;
+    std::vector<double2> spec, tw, tw_tab, c_tab;
     std::vector<double> ring; // the whole past of the input stream (power-of-two ring, zero before the start)
     long long ring_mask = 0;
     int glog_force = -1;
@@ -37,29 +37,36 @@ template <bool PADV>
 void interp_tc(const FusedParams& p, const DstView& dst, const Tile& t, const double* yb, const double* sbank, const int* s_goff,
                const int* s_i, double* s_o)
 {
-    const int n_mu = mma_units(p, s_i[1]), ksteps = p.smaxp >> 2;
-    for (int unit = 0; unit < n_mu; unit++) {
-        double acc[MBU][32][2] = {};
-        for (int ks = 0; ks < ksteps; ks++) {
-            double b[32];
-            for (int lane = 0; lane < 32; lane++) b[lane] = sbank[mma_b_index(p, unit, lane) + ks * 32];
-            for (int i = 0; i < MBU; i++) {
-                double a[32];
-                for (int lane = 0; lane < 32; lane++) {
-                    const int yi = mma_a_index(p, s_goff, s_i, unit, i, lane) + 4 * ks;
-                    a[lane] = PADV ? yb[ylay(yi, p.ysh)] : yb[yi];
-                }
-                for (int lane = 0; lane < 32; lane++) {
-                    const int row = lane >> 2, col = 2 * (lane & 3);
-                    for (int k = 0; k < 4; k++) {
-                        acc[i][lane][0] = fma(a[4 * row + k], b[4 * col + k], acc[i][lane][0]);
-                        acc[i][lane][1] = fma(a[4 * row + k], b[4 * (col + 1) + k], acc[i][lane][1]);
+    MmaTile mt;
+    mt.load(s_i);
+    const int n_groups = (p.out_step + 7) / 8;
+    const int n_mu = mma_units(p, mt.c_cnt), ksteps = p.smaxp >> 2;
+    for (int w = 0; w < HT / 32; w++) { // the kernel deals units to its 8 warps round-robin
+        MmaUnit mu;
+        mu.set(w, n_groups);
+        for (int unit = w; unit < n_mu; unit += HT / 32, mu.advance(HT / 32, n_groups)) {
+            double acc[MBU][32][2] = {};
+            for (int ks = 0; ks < ksteps; ks++) {
+                double b[32];
+                for (int lane = 0; lane < 32; lane++) b[lane] = sbank[mma_b_index(p, mu, lane) + ks * 32];
+                for (int i = 0; i < MBU; i++) {
+                    double a[32];
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int yi = mma_a_index(p, mt, mu, s_goff[mu.g], i, lane) + 4 * ks;
+                        a[lane] = PADV ? yb[ylay(yi, p.ysh)] : yb[yi];
+                    }
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int row = lane >> 2, col = 2 * (lane & 3);
+                        for (int k = 0; k < 4; k++) {
+                            acc[i][lane][0] = fma(a[4 * row + k], b[4 * col + k], acc[i][lane][0]);
+                            acc[i][lane][1] = fma(a[4 * row + k], b[4 * (col + 1) + k], acc[i][lane][1]);
+                        }
                     }
                 }
             }
+            for (int i = 0; i < MBU; i++)
+                for (int lane = 0; lane < 32; lane++) mma_store(p, dst, t.ch, mt, s_o, mu, i, lane, acc[i][lane][0], acc[i][lane][1]);
         }
-        for (int i = 0; i < MBU; i++)
-            for (int lane = 0; lane < 32; lane++) mma_store(p, dst, t.ch, s_i, s_o, unit, i, lane, acc[i][lane][0], acc[i][lane][1]);
     }
 }
 
@@ -109,7 +116,7 @@ void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, con
             }
             const double2 ze = buf[(size_t) fft_pad(slot_of<FN>(FN / 2))];
             for (int ht = 0; ht < HT; ht++)
-                for (int i = 0; i < 4; i++) c_pair(p, buf.data(), c_freq(ht, i), z1[(size_t) ht * 4 + i], z2[(size_t) ht * 4 + i]);
+                for (int i = 0; i < 4; i++) c_pair_tab(p, buf.data(), ht, i, z1[(size_t) ht * 4 + i], z2[(size_t) ht * 4 + i]);
             c_pair(p, buf.data(), FN / 2, ze, ze);
         }
         for (int ht = 0; ht < HT; ht++) inv_pass<16>(buf.data(), tw2, ht);
@@ -178,6 +185,7 @@ void* f2emul_create(double src, double dst, int max_in_len, double tb, double at
     E->B = build_group_bank(E->plan.stages[1], E->tc ? 8 : choose_group_ir(E->plan.stages[1]));
     build_spectrum(E->plan.stages[0], 12, E->spec, E->tw, nullptr);
     E->tw_tab = build_tw_tab(E->tw);
+    E->c_tab = build_c_tab(E->spec, E->tw);
     E->ring.assign((size_t) 1 << 22, 0.0);
     E->ring_mask = ((long long) 1 << 22) - 1;
     E->glog_force = E->tc ? -1 : glog_force;
@@ -205,6 +213,7 @@ int f2emul_process(void* h, const double* x, int l, double* out, int out_cap)
         p.ysh = E.fg.ysh;
         p.spec = E.spec.data();
         p.tw = E.tw.data();
+        p.c_tab = E.c_tab.data();
         p.gbank = E.B.gb.data();
         p.goff = E.B.go.data();
         p.smaxp = E.B.smaxp;
