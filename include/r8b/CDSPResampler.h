@@ -74,14 +74,18 @@ public:
         if (Plan != NULL) r8bgpu_plan_destroy(Plan);
     }
 
-    bool isValid() const { return Plan != NULL; }
+    /// false: the constructor arguments were refused (out-of-range parameters, fprMinPhase ...) or, after the first
+    /// call, no CUDA device / no memory for the batch.  The reference has no such state (R8BASSERT compiles out and
+    /// bad parameters are undefined behaviour); here every accessor of an invalid object returns 0 and every
+    /// process() returns -1, and getLastError() says why.
+    bool isValid() const { return Plan != NULL && !Failed; }
     const char* getLastError() const { return r8bgpu_last_error(); }
     int getNumChannels() const { return Channels; }
     int getMaxOutLen(const int /* MaxInLen */ = 0) const { return Plan ? r8bgpu_plan_max_out_len(Plan) : 0; }
-    int getInLenBeforeOutPos(const int ReqOutPos) const { return r8bgpu_plan_in_len_before_out_pos(Plan, ReqOutPos); }
-    int getInputRequiredForOutput(const int ReqOutSamples) const { return r8bgpu_plan_input_required_for_output(Plan, ReqOutSamples); }
+    int getInLenBeforeOutPos(const int ReqOutPos) const { return Plan ? r8bgpu_plan_in_len_before_out_pos(Plan, ReqOutPos) : 0; }
+    int getInputRequiredForOutput(const int ReqOutSamples) const { return Plan ? r8bgpu_plan_input_required_for_output(Plan, ReqOutSamples) : 0; }
     int getLatency() const { return 0; }
-    double getLatencyFrac() const { return r8bgpu_plan_latency_frac(Plan); }
+    double getLatencyFrac() const { return Plan ? r8bgpu_plan_latency_frac(Plan) : 0.0; }
 
     void clear()
     {
@@ -141,10 +145,14 @@ private:
     int Channels;
     int Dev;
     int MaxInLen;
+    bool Failed = false; // batch creation was tried and refused: do not retry on every call
 
     bool ensure()
     {
-        if (Batch == NULL && Plan != NULL) Batch = r8bgpu_batch_create(Plan, Channels, Dev);
+        if (Batch == NULL && Plan != NULL && !Failed) {
+            Batch = r8bgpu_batch_create(Plan, Channels, Dev);
+            Failed = (Batch == NULL);
+        }
         R8BASSERT(Batch != NULL);
         return Batch != NULL;
     }
@@ -171,6 +179,11 @@ public:
 
     virtual ~CDSPResampler() {}
 
+    /// Not in the reference: see CDSPResamplerBatch::isValid().  An invalid object produces no output: process()
+    /// returns 0 samples, oneshot() zero-fills, getInLenBeforeOutStart() returns 0 -- none of them loops.
+    bool isValid() const { return IsSame || (Impl.isValid() && !Broken); }
+    const char* getLastError() const { return Impl.getLastError(); }
+
     virtual int getInLenBeforeOutPos(const int ReqOutPos) const { return Impl.getInLenBeforeOutPos(ReqOutPos); }
     int getInputRequiredForOutput(const int ReqOutSamples) const { return Impl.getInputRequiredForOutput(ReqOutSamples); }
     virtual int getLatency() const { return 0; }
@@ -186,6 +199,7 @@ public:
             double ins = 0.0;
             double* op;
             outc += process(&ins, 1, op);
+            if (!isValid()) return 0; // a failed object never produces output: do not spin
             if (outc > ReqOutPos) {
                 clear();
                 return inc;
@@ -206,6 +220,7 @@ public:
         op0 = &OutBuf[0];
         const int n = Impl.process(ip0, (size_t) l, l, op0, OutBuf.size(), (int) OutBuf.size());
         R8BASSERT(n >= 0);
+        if (n < 0) Broken = true; // sticky: isValid() turns false, the loops below stop
         return n < 0 ? 0 : n;
     }
 
@@ -229,6 +244,10 @@ public:
             }
             double* res = NULL;
             int produced = process(&chunk[0], n, res);
+            if (!isValid()) { // no device, refused parameters, launch failure: silence instead of an endless loop
+                for (int i = got; i < oplen; i++) op[i] = (Tout) 0;
+                return;
+            }
             if (produced > oplen - got) produced = oplen - got;
             for (int i = 0; i < produced; i++) op[got + i] = (Tout) res[i];
             got += produced;
@@ -241,6 +260,7 @@ private:
     std::vector<double> OutBuf;
     int MaxInLen;
     bool IsSame;
+    bool Broken = false;
 };
 
 class CDSPResampler16 : public CDSPResampler {

@@ -116,6 +116,7 @@ struct StageDev {
     // v2 fused kernel (r8b_fused2.cu): [q][r] twiddle tables for the bulk copy; on the BLOCKCONV stage
     double2* tw_tab = nullptr;
     double2* c_tab = nullptr;   // v2 fused kernel: phase C operands in thread order
+    bool bank_frag_order = false; // grouped bank stored in mma fragment order (only the tensor-path interpolation reads it)
     bool f2_ok = false;
     FusedGeom fgeom;
 };
@@ -463,7 +464,16 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 // the fused kernels: IR consecutive phases share one y window
                 // (the tensor-path interpolation of the v2 kernel works on groups of exactly 8 phases)
                 const bool want_f2 = d.fused_into_prev && i > 0 && !getenv("R8BGPU_FUSED_V1");
-                const GroupBank B = build_group_bank(s, (want_f2 && (b->f2_flags & 4)) ? 8 : choose_group_ir(s));
+                bool tc_bank = want_f2 && (b->f2_flags & 4);
+                GroupBank B = build_group_bank(s, tc_bank ? 8 : choose_group_ir(s), tc_bank);
+                auto f2_fits = [&](const GroupBank& gb) {
+                    return fused2_smem_bytes(gb.n_groups * gb.smaxp * gb.ir, false) <= kFused2SmemMax && gb.n_groups <= 192;
+                };
+                if (tc_bank && !f2_fits(B)) { // the v2 kernel will not run this pair: the v1 kernel reads the plain layout
+                    tc_bank = false;
+                    B = build_group_bank(s, choose_group_ir(s), false);
+                }
+                d.bank_frag_order = tc_bank;
                 const size_t tb = B.off.size() * sizeof(int);
                 if (!cuda_ok(cudaMalloc(&d.phase_off, tb), "cudaMalloc(phase)")) return nullptr;
                 if (!cuda_ok(cudaMalloc(&d.phase_row, tb), "cudaMalloc(phase)")) return nullptr;
@@ -480,7 +490,7 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 b->dev_bytes += B.gb.size() * sizeof(double);
                 d.bank_in_smem = (fused_smem_bytes(d.gbank_smem_len) <= 220 * 1024) ? 1 : 0;
                 // the persistent two-pipeline kernel needs the call's whole bank in shared memory
-                if (want_f2 && fused2_smem_bytes(d.gbank_smem_len, false) <= kFused2SmemMax && (s.out_step + d.ir - 1) / d.ir <= 192)
+                if (want_f2 && f2_fits(B))
                     b->dev[i - 1].f2_ok = true;
             }
         }
@@ -813,7 +823,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.flags = b->f2_flags;
                 p.tw_tab = d.tw_tab;
                 p.c_tab = d.c_tab;
-                if (p.ir != 8) p.flags &= ~4;
+                if (!fd.bank_frag_order) p.flags &= ~4; // (the bank layout decides: see batch_create)
                 p.stage_off = (p.ir == 8 && !(p.flags & 4) && fused2_smem_bytes(p.gbank_smem_len, true) <= kFused2SmemMax &&
                                !getenv("R8BGPU_NO_STAGE")) ? fused2_stage_off(p.gbank_smem_len) : 0;
                 p.glog = fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);

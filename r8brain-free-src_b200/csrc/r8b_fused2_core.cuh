@@ -75,17 +75,22 @@ R8B_HD void gather_tile(double2 (&v)[8], const SrcView& src, const Tile& t, int 
     }
 }
 
-// forward pass 1: radix 8 on registers, NCUR = FN, D = 256; twiddle W_2048^(r q) = W_4096^(r 2q)
+// forward pass 1: radix 8 on registers, NCUR = FN, D = 256; twiddle W_2048^(r q) = W_4096^(r 2q): q = 1, 2, 4 from the tables,
+// the other four as products (see twiddles16)
 R8B_HD void fwd_pass1_r8(double2 (&v)[8], double2* __restrict__ s, const double2* __restrict__ twc,
                          const double2* __restrict__ twf, int r)
 {
     Network<8, +1>::run(v);
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        double2 x = v[bitrev<8>(q)];
-        if (q > 0) x = cmul<+1>(x, tw_pair(twc, twf, r, 2 * q));
-        s[fft_pad(r + q * 256)] = x;
-    }
+    const double2 w1 = tw_pair(twc, twf, r, 2), w2 = tw_pair(twc, twf, r, 4), w4 = tw_pair(twc, twf, r, 8);
+    const double2 w3 = cprod(w1, w2);
+    s[fft_pad(r)] = v[0];
+    s[fft_pad(r + 1 * 256)] = cmul<+1>(v[bitrev<8>(1)], w1);
+    s[fft_pad(r + 2 * 256)] = cmul<+1>(v[bitrev<8>(2)], w2);
+    s[fft_pad(r + 3 * 256)] = cmul<+1>(v[bitrev<8>(3)], w3);
+    s[fft_pad(r + 4 * 256)] = cmul<+1>(v[bitrev<8>(4)], w4);
+    s[fft_pad(r + 5 * 256)] = cmul<+1>(v[bitrev<8>(5)], cprod(w1, w4));
+    s[fft_pad(r + 6 * 256)] = cmul<+1>(v[bitrev<8>(6)], cprod(w2, w4));
+    s[fft_pad(r + 7 * 256)] = cmul<+1>(v[bitrev<8>(7)], cprod(w3, w4));
 }
 
 // C, first half: this thread's four frequency pairs (k, N-k), k <= N/2.  In slot order (k = q1 + 8 q2 + 128 q3,
@@ -143,12 +148,9 @@ R8B_HD void c_pair_tab(const FusedParams& p, double2* __restrict__ buf, int ht, 
 R8B_HD void inv3_load(const double2* __restrict__ buf, const double2* __restrict__ twc, const double2* __restrict__ twf,
                       int g, double2 (&v)[16])
 {
-#pragma unroll
-    for (int q = 0; q < 16; q++) {
-        double2 x = buf[fft_pad(g + q * 256)];
-        if (q > 0) x = cmul<-1>(x, tw_pair(twc, twf, g, q));
-        v[q] = x;
-    }
+    v[0] = buf[fft_pad(g)];
+    twiddles16([&](int q) { return tw_pair(twc, twf, g, q); },
+               [&](int q, double2 w) { v[q] = cmul<-1>(buf[fft_pad(g + q * 256)], w); });
     Network<16, -1>::run(v);
 }
 
@@ -156,11 +158,12 @@ template <bool PADV>
 R8B_HD void y_store(double2* __restrict__ buf, const double2 (&v)[16], int g, long long w, int ysh)
 {
     double* yb = reinterpret_cast<double*>(buf);
+    const bool head = w < 0; // only the first tile of a stream reaches before sample 0 (tile-uniform)
 #pragma unroll
     for (int j = 0; j < 16; j++) {
         const int e = g + j * 256;              // local input-rate position
         double2 x = v[bitrev<16>(j)];
-        if (2 * (w + e) < 0) x = make_double2(0.0, 0.0); // the reference's interpolator starts from silence
+        if (head && w + e < 0) x = make_double2(0.0, 0.0); // the reference's interpolator starts from silence
         if (!PADV) {
             reinterpret_cast<double2*>(yb)[e] = x;
         } else {
@@ -360,7 +363,8 @@ R8B_HD int mma_a_index(const FusedParams& p, const MmaTile& mt, const MmaUnit& u
 }
 
 // offset of the lane's B element at K-step 0 inside the call's bank (K-step ks adds 32*ks)
-R8B_HD int mma_b_index(const FusedParams& p, const MmaUnit& u, int lane) { return u.g * p.smaxp * 8 + (lane & 3) * 8 + (lane >> 2); }
+// (tensor-path bank layout: within a K-step the 32 values sit in fragment order, element n*4 + k = Bp[4 ks + k][n])
+R8B_HD int mma_b_index(const FusedParams& p, const MmaUnit& u, int lane) { return u.g * p.smaxp * 8 + lane; }
 
 // the lane's two results of block i: outputs (cycle, phases 2*(lane%4), +1) of the group
 R8B_HD void mma_store(const FusedParams& p, const DstView& dst, int ch, const MmaTile& mt, double* s_o, const MmaUnit& u, int i, int lane,

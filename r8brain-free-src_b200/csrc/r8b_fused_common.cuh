@@ -37,6 +37,39 @@ R8B_HD double2 tw_pair(const double2* __restrict__ tw2t, const double2* __restri
     return make_double2(fma(c.x, f.x, -c.y * f.y), fma(c.x, f.y, c.y * f.x));
 }
 
+// Twiddles of one radix-16 butterfly, W^(r q) for q = 1..15, from FOUR table reads (q = 1, 2, 4, 8) and eleven
+// products W^(r (a+b)) = W^(r a) W^(r b).  The passes are bound by shared-memory wavefronts, not by the fp64 pipe,
+// and a twiddle read costs as much as a data read.  A derived twiddle carries one to three extra roundings (q = 15);
+// measured end to end (cfg 2 and 3, rms error against the reference, parity bar 4 eps): fifteen reads 2.53 eps, six
+// reads + nine single products 2.55, this variant 2.58.  `ld(q)` fetches a table value; use(q, w) is called once per
+// q, in the order (q, q + 8), so only w1, w2, w3, w4, w8 stay live.
+R8B_HD double2 cprod(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
+
+template <typename Ld, typename Use>
+R8B_HD void twiddles16(Ld ld, Use use)
+{
+    const double2 w8 = ld(8), w1 = ld(1), w2 = ld(2), w4 = ld(4);
+    use(8, w8);
+    use(1, w1);
+    use(9, cprod(w1, w8));
+    use(2, w2);
+    use(10, cprod(w2, w8));
+    const double2 w3 = cprod(w1, w2);
+    use(3, w3);
+    use(11, cprod(w3, w8));
+    use(4, w4);
+    use(12, cprod(w4, w8));
+    const double2 w5 = cprod(w1, w4);
+    use(5, w5);
+    use(13, cprod(w5, w8));
+    const double2 w6 = cprod(w2, w4);
+    use(6, w6);
+    use(14, cprod(w6, w8));
+    const double2 w7 = cprod(w3, w4);
+    use(7, w7);
+    use(15, cprod(w7, w8));
+}
+
 // One radix-16 DIF pass over blocks of NCUR points in padded shared memory; butterfly g of M/16.
 template <int NCUR>
 R8B_HD void fwd_pass(double2* __restrict__ s, const double2* __restrict__ tw2_s, int g)
@@ -48,11 +81,13 @@ R8B_HD void fwd_pass(double2* __restrict__ s, const double2* __restrict__ tw2_s,
 #pragma unroll
     for (int j = 0; j < 16; j++) v[j] = s[fft_pad(base + j * D)];
     Network<16, +1>::run(v);
+    s[fft_pad(base)] = v[0];
+    if (D > 1) { // NCUR == 256: W_256^(r q), [q][r] layout
+        twiddles16([&](int q) { return tw2_s[q * 16 + r]; },
+                   [&](int q, double2 w) { s[fft_pad(base + q * D)] = cmul<+1>(v[bitrev<16>(q)], w); });
+    } else {
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
-        double2 x = v[bitrev<16>(q)];
-        if (D > 1 && q > 0) x = cmul<+1>(x, tw2_s[q * 16 + r]); // NCUR == 256: W_256^(r q), [q][r] layout
-        s[fft_pad(base + q * D)] = x;
+        for (int q = 1; q < 16; q++) s[fft_pad(base + q * D)] = v[bitrev<16>(q)];
     }
 }
 
@@ -63,11 +98,13 @@ R8B_HD void inv_pass(double2* __restrict__ s, const double2* __restrict__ tw2_s,
     const int blk = g / D, r = g % D;
     const int base = blk * NCUR + r;
     double2 v[16];
+    v[0] = s[fft_pad(base)];
+    if (D > 1) {
+        twiddles16([&](int q) { return tw2_s[q * 16 + r]; },
+                   [&](int q, double2 w) { v[q] = cmul<-1>(s[fft_pad(base + q * D)], w); });
+    } else {
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
-        double2 x = s[fft_pad(base + q * D)];
-        if (D > 1 && q > 0) x = cmul<-1>(x, tw2_s[q * 16 + r]);
-        v[q] = x;
+        for (int q = 1; q < 16; q++) v[q] = s[fft_pad(base + q * D)];
     }
     Network<16, -1>::run(v);
 #pragma unroll

@@ -152,7 +152,7 @@ int choose_group_ir(const StageDesc& s)
     return ir;
 }
 
-GroupBank build_group_bank(const StageDesc& s, int ir)
+GroupBank build_group_bank(const StageDesc& s, int ir, bool frag_order)
 {
     GroupBank B;
     const int os = s.out_step, flen = s.bank.filter_len;
@@ -179,7 +179,11 @@ GroupBank build_group_bank(const StageDesc& s, int ir)
             const int pr = r0 + r;
             const int dr = offx(pr) - offx(r0);
             const double* rowp = s.bank.table.data() + (size_t) B.row[(size_t) (pr % os)] * flen;
-            for (int i = 0; i < flen; i++) B.gb[((size_t) r0 * B.smaxp + dr + i) * ir + r] = rowp[i];
+            for (int i = 0; i < flen; i++) {
+                const int tap = dr + i;
+                const size_t at = frag_order ? (size_t) (tap & ~3) * 8 + (size_t) r * 4 + (tap & 3) : (size_t) tap * ir + r;
+                B.gb[(size_t) r0 * B.smaxp * ir + at] = rowp[i];
+            }
         }
     }
     return B;

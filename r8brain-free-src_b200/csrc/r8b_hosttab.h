@@ -39,7 +39,9 @@ struct GroupBank {
     std::vector<int> off, row; // per phase: window offset, bank row
 };
 int choose_group_ir(const StageDesc& frac);
-GroupBank build_group_bank(const StageDesc& frac, int ir);
+// frag_order (ir == 8 only): within every block of 4 taps the 32 values are stored as [phase][tap % 4] -- the B-fragment
+// order of mma.sync m8n8k4, so a warp's load of one K-step is 256 contiguous bytes
+GroupBank build_group_bank(const StageDesc& frac, int ir, bool frag_order = false);
 
 // Whole-stepping call: the fields of FusedParams that follow from the interpolator stage and this call's output
 // range [e0, e1) alone (positions are indices of the 2x-rate stream; p_lo even).

@@ -182,7 +182,7 @@ void* f2emul_create(double src, double dst, int max_in_len, double tb, double at
     }
     E->sched.init(&E->plan);
     E->tc = glog_force == 8;
-    E->B = build_group_bank(E->plan.stages[1], E->tc ? 8 : choose_group_ir(E->plan.stages[1]));
+    E->B = build_group_bank(E->plan.stages[1], E->tc ? 8 : choose_group_ir(E->plan.stages[1]), E->tc);
     build_spectrum(E->plan.stages[0], 12, E->spec, E->tw, nullptr);
     E->tw_tab = build_tw_tab(E->tw);
     E->c_tab = build_c_tab(E->spec, E->tw);

@@ -17,6 +17,23 @@ int main(int argc, char** argv)
                rs.getLatencyFrac());
         return 0;
     }
+    if (argc == 2 && strcmp(argv[1], "--failures") == 0) {
+        // objects that cannot work must say so and must not hang: (a) a refused plan (minimum phase), (b) on a box
+        // without a CUDA device, a valid plan whose batch cannot be created
+        r8b::CDSPResampler bad(44100.0, 96000.0, 1024, 2.0, 180.15, r8b::fprMinPhase);
+        float out[64];
+        short in[16] = {1, 2, 3};
+        bad.oneshot(in, 16, out, 64);
+        int zeros = 0;
+        for (int i = 0; i < 64; i++) zeros += out[i] == 0.0f;
+        printf("%d %d %d %d %d\n", (int) bad.isValid(), bad.getInLenBeforeOutStart(0), zeros, bad.getInLenBeforeOutPos(0),
+               bad.getInputRequiredForOutput(10));
+        r8b::CDSPResampler24 ok(44100.0, 96000.0, 1024);
+        const int before = (int) ok.isValid();
+        const int start = ok.getInLenBeforeOutStart(0); // terminates with or without a device
+        printf("%d %d %d\n", before, (int) ok.isValid(), start);
+        return 0;
+    }
     if (argc != 8) return 2;
     const int n_ch = atoi(argv[3]), frames = atoi(argv[4]), block = atoi(argv[7]);
     const double src = atof(argv[5]), dst = atof(argv[6]);

@@ -35,6 +35,21 @@ def test_shim_compiles_and_plans(pkg, ref):
                                                        r.input_required_for_output(1000)]
 
 
+def test_shim_failures_do_not_hang(pkg, ref):
+    """A refused plan / a missing device must surface through isValid() and must never spin (the reference has no
+    error channel; its loops in oneshot() / getInLenBeforeOutStart() assume process() always makes progress)."""
+    exe = build_demo(pkg)
+    out = subprocess.run([exe, "--failures"], capture_output=True, text=True, check=True, timeout=120).stdout.split("\n")
+    valid, start, zeros, a, b = [int(t) for t in out[0].split()]
+    assert (valid, start, zeros, a, b) == (0, 0, 64, 0, 0)
+    before, after, start2 = [int(t) for t in out[1].split()]
+    assert before == 1
+    if pkg.device_count() < 1:
+        assert (after, start2) == (0, 0)
+    else:
+        assert after == 1 and start2 == ref.Resampler(44100.0, 96000.0, 1024, 2.0, 180.15).in_len_before_out_start(0)
+
+
 @pytest.mark.gpu
 def test_shim_process_matches_reference(pkg, ref, tmp_path):
     exe = build_demo(pkg)
