@@ -110,8 +110,24 @@ R8BGPU_API int r8bgpu_plan_simulate(const r8bgpu_plan* plan, const int* lens, in
 /* ---- batch (GPU) ------------------------------------------------------------------------- */
 
 R8BGPU_API int r8bgpu_device_count(void);
-/* device < 0: the current CUDA device. */
+/* device >= 0: that CUDA device.  R8BGPU_DEVICE_ALL (-1): every visible device -- the channels are sharded
+ * contiguously, ceil(n/G) per GPU, and each shard is an ordinary single-device batch driven by its own worker thread
+ * (bound to the GPU's NUMA node), stream set and PCIe link; there is no device-to-device traffic.  Such a batch takes
+ * HOST buffers (r8bgpu_batch_process_host / _host_fmt); device buffers go to the shards (r8bgpu_batch_shard()).  With
+ * one visible device, or one channel, this is an ordinary batch.  R8BGPU_DEVICE_CURRENT (-2): the current device.
+ * Replaces the caller-side loop over per-channel objects spread over threads (example.cpp:30-67). */
+#define R8BGPU_DEVICE_ALL (-1)
+#define R8BGPU_DEVICE_CURRENT (-2)
 R8BGPU_API r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int device);
+/* Shards of a batch (1 for a single-device batch): device, channel range and NUMA node (-1: unknown / one node). */
+R8BGPU_API int r8bgpu_batch_shard_count(const r8bgpu_batch* batch);
+R8BGPU_API int r8bgpu_batch_shard_info(const r8bgpu_batch* batch, int shard, int* device, int* first_channel,
+                                       int* n_channels, int* numa_node);
+/* The single-device batch behind shard `shard` (owned by `batch`; for device-pointer calls on its GPU). */
+R8BGPU_API r8bgpu_batch* r8bgpu_batch_shard(r8bgpu_batch* batch, int shard);
+/* Page-locked planar host buffer [channels][samples_per_channel] of `sample_bytes`-wide samples whose rows sit on the
+ * NUMA node of the GPU that owns the channel (mmap + mbind + cudaHostRegister); free with r8bgpu_host_free(). */
+R8BGPU_API void* r8bgpu_batch_host_alloc(const r8bgpu_batch* batch, size_t samples_per_channel, int sample_bytes);
 R8BGPU_API void r8bgpu_batch_destroy(r8bgpu_batch* batch);
 R8BGPU_API int r8bgpu_batch_clear(r8bgpu_batch* batch);
 R8BGPU_API int r8bgpu_batch_channels(const r8bgpu_batch* batch);

@@ -57,6 +57,10 @@ _SYMBOLS = {
     "r8bgpu_device_count": (C.c_int, []),
     "r8bgpu_batch_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "r8bgpu_batch_destroy": (None, [C.c_void_p]),
+    "r8bgpu_batch_shard_count": (C.c_int, [C.c_void_p]),
+    "r8bgpu_batch_shard_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "r8bgpu_batch_shard": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "r8bgpu_batch_host_alloc": (C.c_void_p, [C.c_void_p, C.c_size_t, C.c_int]),
     "r8bgpu_batch_clear": (C.c_int, [C.c_void_p]),
     "r8bgpu_batch_channels": (C.c_int, [C.c_void_p]),
     "r8bgpu_batch_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -206,10 +210,22 @@ class Plan:
         return list(o)
 
 
-class Batch:
-    """n_channels independent streams resampled in lock-step on one GPU (device pointers)."""
+DEVICE_ALL, DEVICE_CURRENT = -1, -2
+_host_allocs = {}
 
-    def __init__(self, plan, n_channels, device=-1):
+
+def host_free(arr):
+    """Release an array from Batch.host_alloc()."""
+    p = _host_allocs.pop(arr.ctypes.data, None)
+    if p is not None:
+        lib().r8bgpu_host_free(C.c_void_p(p))
+
+
+class Batch:
+    """n_channels independent streams resampled in lock-step: on one GPU (device >= 0, or DEVICE_CURRENT), or sharded
+    over every visible GPU behind the C-ABI (DEVICE_ALL: host-buffer calls only)."""
+
+    def __init__(self, plan, n_channels, device=-2):
         self.plan = plan
         self.n_channels = int(n_channels)
         self._h = lib().r8bgpu_batch_create(plan._h, self.n_channels, int(device))
@@ -220,6 +236,31 @@ class Batch:
         if getattr(self, "_h", None) and _lib is not None:
             _lib.r8bgpu_batch_destroy(self._h)
             self._h = None
+
+    def shards(self):
+        """[(device, first_channel, n_channels, numa_node)] -- one entry for a single-device batch."""
+        out = []
+        for i in range(lib().r8bgpu_batch_shard_count(self._h)):
+            d, c0, n, node = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+            if lib().r8bgpu_batch_shard_info(self._h, i, C.byref(d), C.byref(c0), C.byref(n), C.byref(node)) != 0:
+                raise R8bGpuError(_err())
+            out.append((d.value, c0.value, n.value, node.value))
+        return out
+
+    def host_alloc(self, samples_per_channel, dtype="float64"):
+        """Pinned planar [n_channels, samples_per_channel] numpy array, rows on the NUMA node of the owning GPU.
+        Keep the returned array alive while in use; release with host_free(arr)."""
+        import numpy as np
+        dt = np.dtype(dtype)
+        p = lib().r8bgpu_batch_host_alloc(self._h, int(samples_per_channel), dt.itemsize)
+        if not p:
+            raise R8bGpuError(_err())
+        n = self.n_channels * int(samples_per_channel)
+        buf = (C.c_char * (n * dt.itemsize)).from_address(p)
+        arr = np.frombuffer(buf, dtype=dt, count=n).reshape(self.n_channels, int(samples_per_channel))
+        arr.flags.writeable = True
+        _host_allocs[arr.ctypes.data] = p
+        return arr
 
     def clear(self):
         if lib().r8bgpu_batch_clear(self._h) != 0:

@@ -11,8 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libr8bgpu.so")
-SOURCES = ["r8b_capi.cu", "r8b_kernels.cu", "r8b_fused.cu", "r8b_fused2.cu", "r8b_format.cu", "r8b_plan.cpp", "r8b_design.cpp", "r8b_hosttab.cpp"]
-HEADERS = ["r8b_fft.cuh", "r8b_interp.cuh", "r8b_fused_common.cuh", "r8b_fused2_core.cuh", "r8b_hbfuse.cuh", "r8b_kernels.h", "r8b_plan.h", "r8b_hosttab.h", "r8b_design.h", "r8b_tables.inc",
+SOURCES = ["r8b_capi.cu", "r8b_kernels.cu", "r8b_fused.cu", "r8b_fused2.cu", "r8b_format.cu", "r8b_plan.cpp", "r8b_design.cpp", "r8b_hosttab.cpp", "r8b_multi.cpp"]
+HEADERS = ["r8b_fft.cuh", "r8b_interp.cuh", "r8b_fused_common.cuh", "r8b_fused2_core.cuh", "r8b_hbfuse.cuh", "r8b_kernels.h", "r8b_plan.h", "r8b_hosttab.h", "r8b_multi.h", "r8b_design.h", "r8b_tables.inc",
            os.path.join("..", "..", "include", "r8bgpu.h")]
 
 NVCC_FLAGS = [

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -22,6 +23,7 @@
 #include "r8b_fft.cuh"
 #include "r8b_hosttab.h"
 #include "r8b_kernels.h"
+#include "r8b_multi.h"
 #include "r8b_plan.h"
 
 using namespace r8bgpu;
@@ -127,7 +129,17 @@ struct r8bgpu_plan {
     Plan p;
 };
 
+// A multi-device batch (r8bgpu_batch_create(plan, n, -1) on a box with several GPUs) is a FRONT: it owns no device
+// state, only one ordinary single-device batch per shard (contiguous channel ranges) and the worker threads that
+// drive them side by side (r8b_multi.h).
+struct ShardFront {
+    std::vector<r8bgpu_batch*> shards;
+    std::vector<int> ch0, device, numa;
+    std::unique_ptr<ShardPool> pool;
+};
+
 struct r8bgpu_batch {
+    std::unique_ptr<ShardFront> front; // non-null: multi-device front (everything below except plan/n_ch is unused)
     const Plan* plan = nullptr;
     Plan plan_copy; // batches own a copy so the plan handle may be destroyed first
     int n_ch = 0;
@@ -162,6 +174,11 @@ struct r8bgpu_batch {
 
     ~r8bgpu_batch()
     {
+        if (front) {
+            front->pool.reset();
+            for (r8bgpu_batch* sb : front->shards) delete sb;
+            return;
+        }
         DeviceGuard g(device);
         if (prof != nullptr) {
             unsigned long long h[10] = {};
@@ -346,6 +363,51 @@ int r8bgpu_device_count(void)
     return n;
 }
 
+static r8bgpu_batch* create_front(const r8bgpu_plan* plan, int n_channels, int n_sh, int ndev)
+{
+    std::unique_ptr<r8bgpu_batch> b(new r8bgpu_batch);
+    b->plan_copy = plan->p;
+    b->plan = &b->plan_copy;
+    b->n_ch = n_channels;
+    b->device = -1;
+    b->front.reset(new ShardFront);
+    ShardFront& F = *b->front;
+    const int per = (n_channels + n_sh - 1) / n_sh; // ceil(C / G) channels per shard, the last one takes the rest
+    for (int s = 0; s * per < n_channels; s++) {
+        const int c0 = s * per, n = std::min(per, n_channels - c0), dev = s % ndev;
+        r8bgpu_batch* sb = r8bgpu_batch_create(plan, n, dev);
+        if (sb == nullptr) return nullptr; // (b's destructor releases the shards made so far)
+        F.shards.push_back(sb);
+        F.ch0.push_back(c0);
+        F.device.push_back(dev);
+        F.numa.push_back(gpu_numa_node(dev));
+    }
+    F.pool.reset(new ShardPool(F.numa));
+    return b.release();
+}
+
+// run fn(shard batch, shard index) on every shard's worker thread; all shards see the same block lengths, so they
+// return the same count.  Any failure fails the call (the shards' schedules then disagree: the caller must clear()).
+static int front_run(r8bgpu_batch* b, const std::function<int(r8bgpu_batch*, int)>& fn)
+{
+    ShardFront& F = *b->front;
+    std::vector<std::string> errs;
+    const std::function<int(int)> job = [&](int s) { return fn(F.shards[(size_t) s], s); };
+    const std::function<std::string()> err = [] { return g_err; };
+    const std::vector<int> r = F.pool->run_all(job, &errs, err);
+    for (size_t s = 0; s < r.size(); s++)
+        if (r[s] < 0) {
+            set_err("shard " + std::to_string(s) + " (device " + std::to_string(F.device[s]) + "): " + errs[s]);
+            return -1;
+        }
+    for (size_t s = 1; s < r.size(); s++)
+        if (r[s] != r[0]) {
+            set_err("multi-device batch: shards disagree on the output count");
+            return -1;
+        }
+    return r.empty() ? 0 : r[0];
+}
+
 r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int device)
 {
     if (plan == nullptr || n_channels <= 0 || n_channels > 65535) {
@@ -356,6 +418,16 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
     if (!cuda_ok(cudaGetDeviceCount(&ndev), "batch_create: cudaGetDeviceCount") || ndev == 0) {
         if (g_err.empty()) set_err("batch_create: no CUDA device (this engine has no CPU fallback)");
         return nullptr;
+    }
+    if (device == R8BGPU_DEVICE_ALL) {
+        // shard over every visible device (R8BGPU_FORCE_SHARDS=n: n shards dealt round-robin to the devices -- lets a
+        // one-GPU box exercise the multi-device path)
+        int n_sh = ndev;
+        if (const char* e = getenv("R8BGPU_FORCE_SHARDS")) n_sh = atoi(e) > 0 ? atoi(e) : ndev;
+        if (n_sh > n_channels) n_sh = n_channels;
+        if (n_sh > 1) return create_front(plan, n_channels, n_sh, ndev);
+        device = 0;
+        if (ndev > 1 && !cuda_ok(cudaGetDevice(&device), "batch_create: cudaGetDevice")) return nullptr;
     }
     if (device < 0 && !cuda_ok(cudaGetDevice(&device), "batch_create: cudaGetDevice")) return nullptr;
     if (device >= ndev) {
@@ -505,11 +577,76 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
 
 void r8bgpu_batch_destroy(r8bgpu_batch* batch) { delete batch; }
 int r8bgpu_batch_channels(const r8bgpu_batch* b) { return b->n_ch; }
-unsigned long long r8bgpu_batch_kernel_launches(const r8bgpu_batch* b) { return b->launches; }
-unsigned long long r8bgpu_batch_device_bytes(const r8bgpu_batch* b) { return b->dev_bytes; }
+unsigned long long r8bgpu_batch_kernel_launches(const r8bgpu_batch* b)
+{
+    if (!b->front) return b->launches;
+    unsigned long long n = 0;
+    for (const r8bgpu_batch* sb : b->front->shards) n += sb->launches;
+    return n;
+}
+unsigned long long r8bgpu_batch_device_bytes(const r8bgpu_batch* b)
+{
+    if (!b->front) return b->dev_bytes;
+    unsigned long long n = 0;
+    for (const r8bgpu_batch* sb : b->front->shards) n += sb->dev_bytes;
+    return n;
+}
+int r8bgpu_batch_shard_count(const r8bgpu_batch* b) { return b->front ? (int) b->front->shards.size() : 1; }
+int r8bgpu_batch_shard_info(const r8bgpu_batch* b, int shard, int* device, int* first_channel, int* n_channels, int* numa_node)
+{
+    if (shard < 0 || shard >= r8bgpu_batch_shard_count(b)) {
+        set_err("batch_shard_info: shard index out of range");
+        return -1;
+    }
+    if (!b->front) {
+        if (device) *device = b->device;
+        if (first_channel) *first_channel = 0;
+        if (n_channels) *n_channels = b->n_ch;
+        if (numa_node) *numa_node = gpu_numa_node(b->device);
+        return 0;
+    }
+    const ShardFront& F = *b->front;
+    if (device) *device = F.device[(size_t) shard];
+    if (first_channel) *first_channel = F.ch0[(size_t) shard];
+    if (n_channels) *n_channels = F.shards[(size_t) shard]->n_ch;
+    if (numa_node) *numa_node = F.numa[(size_t) shard];
+    return 0;
+}
+r8bgpu_batch* r8bgpu_batch_shard(r8bgpu_batch* b, int shard)
+{
+    if (shard < 0 || shard >= r8bgpu_batch_shard_count(b)) {
+        set_err("batch_shard: shard index out of range");
+        return nullptr;
+    }
+    return b->front ? b->front->shards[(size_t) shard] : b;
+}
+
+void* r8bgpu_batch_host_alloc(const r8bgpu_batch* b, size_t samples_per_channel, int sample_bytes)
+{
+    if (b == nullptr || sample_bytes <= 0 || samples_per_channel == 0) {
+        set_err("batch_host_alloc: bad arguments");
+        return nullptr;
+    }
+    const size_t row = samples_per_channel * (size_t) sample_bytes;
+    std::vector<NumaRange> ranges;
+    const int n_sh = r8bgpu_batch_shard_count(b);
+    for (int s = 0; s < n_sh; s++) {
+        int c0 = 0, n = 0, node = -1;
+        r8bgpu_batch_shard_info(b, s, nullptr, &c0, &n, &node);
+        ranges.push_back({(size_t) c0 * row, (size_t) n * row, node});
+    }
+    void* p = numa_host_alloc(row * (size_t) b->n_ch, ranges);
+    if (p == nullptr) set_err("batch_host_alloc: mmap / cudaHostRegister failed");
+    return p;
+}
 
 int r8bgpu_batch_set_timing(r8bgpu_batch* b, int enable)
 {
+    if (b->front) {
+        int rc = 0;
+        for (r8bgpu_batch* sb : b->front->shards) rc |= r8bgpu_batch_set_timing(sb, enable);
+        return rc;
+    }
     DeviceGuard g(b->device);
     for (auto& e : b->events) {
         cudaEventDestroy(e.a);
@@ -526,6 +663,15 @@ int r8bgpu_batch_set_timing(r8bgpu_batch* b, int enable)
 // accumulated device time (ms) of `stage` since timing was enabled; *launches = kernel launches.
 double r8bgpu_batch_stage_time_ms(r8bgpu_batch* b, int stage, unsigned long long* launches)
 {
+    if (b->front) { // the shards run side by side: report the slowest one
+        double worst = 0.0;
+        for (r8bgpu_batch* sb : b->front->shards) {
+            const double t = r8bgpu_batch_stage_time_ms(sb, stage, launches);
+            if (t < 0.0) return t;
+            if (t > worst) worst = t;
+        }
+        return worst;
+    }
     if (stage < 0 || stage >= (int) b->stage_ms.size()) {
         set_err("stage_time_ms: timing not enabled or bad stage");
         return -1.0;
@@ -550,6 +696,7 @@ double r8bgpu_batch_stage_time_ms(r8bgpu_batch* b, int stage, unsigned long long
 // (0 = this stage is folded into the kernel of an earlier stage).
 int r8bgpu_batch_stage_kernel(const r8bgpu_batch* b, int stage, char* name, int cap)
 {
+    if (b->front) return r8bgpu_batch_stage_kernel(b->front->shards[0], stage, name, cap);
     if (stage < 0 || stage >= (int) b->plan->stages.size()) {
         set_err("stage_kernel: bad stage index");
         return -1;
@@ -585,12 +732,22 @@ int r8bgpu_batch_stage_kernel(const r8bgpu_batch* b, int stage, char* name, int 
 
 int r8bgpu_batch_set_stream(r8bgpu_batch* b, void* stream)
 {
+    if (b->front) {
+        if (stream == nullptr) return 0;
+        set_err("batch_set_stream: a multi-device batch has one stream per shard (use r8bgpu_batch_shard())");
+        return -1;
+    }
     b->stream = (cudaStream_t) stream;
     return 0;
 }
 
 int r8bgpu_batch_clear(r8bgpu_batch* b)
 {
+    if (b->front) {
+        int rc = 0;
+        for (r8bgpu_batch* sb : b->front->shards) rc |= r8bgpu_batch_clear(sb);
+        return rc == 0 ? 0 : -1;
+    }
     DeviceGuard g(b->device);
     b->sched.clear();
     for (auto& d : b->dev) {
@@ -607,6 +764,11 @@ int r8bgpu_batch_clear(r8bgpu_batch* b)
 
 int r8bgpu_batch_sync(r8bgpu_batch* b)
 {
+    if (b->front) {
+        int rc = 0;
+        for (r8bgpu_batch* sb : b->front->shards) rc |= r8bgpu_batch_sync(sb);
+        return rc == 0 ? 0 : -1;
+    }
     DeviceGuard g(b->device);
     return cuda_ok(cudaStreamSynchronize(b->stream), "batch_sync") ? 0 : -1;
 }
@@ -937,6 +1099,10 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
         set_err("batch_process: null input");
         return -1;
     }
+    if (b->front) {
+        set_err("batch_process: device buffers live on one GPU; call the shards of a multi-device batch (r8bgpu_batch_shard())");
+        return -1;
+    }
     DeviceGuard g(b->device);
     const Plan& P = *b->plan;
     const cudaStream_t st = b->stream;
@@ -1024,8 +1190,28 @@ static bool check_buffer(const r8bgpu_batch* b, const r8bgpu_buffer* d, const ch
 // is a self-contained sub-batch).  Staging buffers are per channel, so groups never alias.
 // Narrow / interleaved sample formats cross PCIe as they are and are widened (narrowed) on the
 // device by r8b_format.cu, in the compute stage of the same pipeline.
+static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, const r8bgpu_buffer& out, int out_cap);
+
+// every shard processes its own channel range of the caller's buffers on its own thread, stream set and PCIe link
+static int process_host_front(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, const r8bgpu_buffer& out, int out_cap)
+{
+    const ShardFront& F = *b->front;
+    auto view = [](const r8bgpu_buffer& d, int c0) {
+        r8bgpu_buffer v = d;
+        if (d.data != nullptr) {
+            const size_t e = (size_t) format_bytes(d.format);
+            v.data = (unsigned char*) d.data + (d.interleaved ? (size_t) c0 * e : (size_t) c0 * d.stride * e);
+        }
+        return v;
+    };
+    return front_run(b, [&](r8bgpu_batch* sb, int s) {
+        return process_host_impl(sb, view(in, F.ch0[(size_t) s]), l, view(out, F.ch0[(size_t) s]), out_cap);
+    });
+}
+
 static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, const r8bgpu_buffer& out, int out_cap)
 {
+    if (b->front) return process_host_front(b, in, l, out, out_cap);
     if (l < 0 || l > b->plan->max_in_len) {
         set_err("batch_process_host: l must be in [0, MaxInLen]");
         return -1;
@@ -1165,6 +1351,10 @@ int r8bgpu_batch_process_fmt(r8bgpu_batch* b, const r8bgpu_buffer* d_in, int l, 
         set_err("batch_process_fmt: null batch");
         return -1;
     }
+    if (b->front) {
+        set_err("batch_process_fmt: device buffers live on one GPU; call the shards of a multi-device batch (r8bgpu_batch_shard())");
+        return -1;
+    }
     if (!check_buffer(b, d_in, "batch_process_fmt(in)") || !check_buffer(b, d_out, "batch_process_fmt(out)")) return -1;
     const bool in_plain = buffer_is_plain(*d_in), out_plain = buffer_is_plain(*d_out);
     if (in_plain && out_plain)
@@ -1247,7 +1437,8 @@ void* r8bgpu_host_alloc(size_t bytes)
 
 void r8bgpu_host_free(void* p)
 {
-    if (p != nullptr) cudaFreeHost(p);
+    if (p == nullptr) return;
+    if (!numa_host_free(p)) cudaFreeHost(p);
 }
 
 } // extern "C"
