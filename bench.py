@@ -133,6 +133,26 @@ def host_threads():
     return max(1, n)
 
 
+def bind_to_numa_node(node):
+    """Pin this process to the CPUs of `node` (inside its current affinity mask).  Returns True when bound."""
+    if node is None or node < 0:
+        return False
+    try:
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except (OSError, ValueError):
+        return False
+
+
 def synth_block(n_ch, block, seed):
     """Planar fp64 white noise in [-1,1), per-channel stream."""
     import numpy as np
@@ -202,6 +222,7 @@ def main():
     ap.add_argument("--channels", type=int, default=0, help="channels per GPU (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-scatter", action="store_true", help="skip the NCCL scatter/gather leg (N > 1)")
     args = ap.parse_args()
 
     src, dst, atten, tb, extfft, def_ch = WORKLOADS[args.workload]
@@ -264,6 +285,10 @@ def main():
 
     plan = pkg.Plan(src, dst, BLOCK, tb, atten, extfft=extfft)
     batch = pkg.Batch(plan, n_ch, local_rank)
+    # this rank's thread and its pinned host buffers belong on the socket its GPU hangs off (two-socket boxes: GPUs 4-7 sit
+    # on NUMA node 1; unbound, every rank's staging lands on node 0 and the end-to-end rate at N = 8 drops by a third)
+    numa_node = batch.shards()[0][3]
+    numa_bound = bind_to_numa_node(numa_node)
     cap = (plan.max_out_len + 7) // 8 * 8  # rows start 64-byte aligned
     # Two distinct input blocks alternate so that no step re-reads a block that could sit in L2.
     xs = [torch.from_numpy(synth_block(n_ch, BLOCK, 1000 + 17 * rank + i)).to(dev) for i in range(2)]
@@ -396,8 +421,13 @@ def main():
     # ---- end to end through the host-pointer C-ABI call (pinned host buffers)
     e2e = None
     if not args.no_e2e:
-        hx = [torch.from_numpy(synth_block(n_ch, BLOCK, 2000 + i)).pin_memory() for i in range(2)]
-        hy = torch.empty((n_ch, cap), dtype=torch.float64).pin_memory()
+        # pinned buffers placed on the GPU's NUMA node (r8bgpu_batch_host_alloc: mmap + mbind + cudaHostRegister)
+        hx = []
+        for i in range(2):
+            a = batch.host_alloc(BLOCK)
+            a[:] = synth_block(n_ch, BLOCK, 2000 + i)
+            hx.append(torch.from_numpy(a))
+        hy = torch.from_numpy(batch.host_alloc(cap))
         batch.set_stream(None)
         ke = max(3, min(K, 8))
         for i in range(2):
@@ -415,7 +445,9 @@ def main():
             t_e2e = float(t.item())
         e2e = {"value": 1e-6 * world * n_ch * BLOCK * ke / t_e2e, "unit": "Msamples/s",
                "h2d_bytes_per_step": n_ch * BLOCK * 8, "d2h_bytes_per_step": int(n_ch * (outs / ke) * 8),
-               "steps": ke, "api": "r8bgpu_batch_process_host (pinned host in/out, sync per call)"}
+               "steps": ke, "api": "r8bgpu_batch_process_host (pinned host in/out, sync per call)",
+               "h2d_gbs_per_gpu": n_ch * BLOCK * 8 * ke / t_e2e / 1e9, "d2h_gbs_per_gpu": n_ch * (outs / ke) * 8 * ke / t_e2e / 1e9,
+               "numa_node": numa_node, "numa_bound": numa_bound}
 
         if world == 1:
             # same call with float32 planar host buffers (r8bgpu_batch_process_host_fmt): what a caller holding
@@ -432,6 +464,39 @@ def main():
             torch.cuda.synchronize(dev)
             e2e["float32_io"] = {"value": 1e-6 * n_ch * BLOCK * ke / (time.perf_counter() - t0), "unit": "Msamples/s",
                                  "api": "r8bgpu_batch_process_host_fmt (R8BGPU_F32 planar in/out)"}
+
+    # ---- NCCL scatter / gather of ONE buffer that lives on rank 0: timed apart from the kernels
+    scatter = None
+    if dist is not None and not args.no_scatter:
+        par = __import__("r8brain_free_src_b200.parallel", fromlist=["x"])
+        total_ch = n_ch * world
+        full_in = torch.from_numpy(synth_block(total_ch, BLOCK, 4000)).to(dev) if rank == 0 else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        t_sc, t_pr, t_ga = [], [], []
+        for it in range(3):
+            barrier()
+            ev[0].record(stream)
+            mine = par.scatter_channels(full_in, total_ch, BLOCK, dist, device=dev, dtype=torch.float64)
+            ev[1].record(stream)
+            n_sc = batch.process_ptr(mine.data_ptr(), BLOCK, BLOCK, out.data_ptr(), cap, cap)
+            ev[2].record(stream)
+            back = par.gather_channels(out[:, :n_sc].contiguous(), total_ch, dist)
+            ev[3].record(stream)
+            barrier()
+            if it > 0:  # first round connects the NCCL peers
+                t_sc.append(ev[0].elapsed_time(ev[1]))
+                t_pr.append(ev[1].elapsed_time(ev[2]))
+                t_ga.append(ev[2].elapsed_time(ev[3]))
+            del back
+        tt = torch.tensor([min(t_sc), min(t_pr), min(t_ga)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        scatter = {"scatter_ms": float(tt[0]), "process_ms": float(tt[1]), "gather_ms": float(tt[2]),
+                   "scatter_bytes": (world - 1) * n_ch * BLOCK * 8, "gather_bytes": int((world - 1) * n_ch * n_sc * 8),
+                   "scatter_gbs": (world - 1) * n_ch * BLOCK * 8 / (float(tt[0]) * 1e-3) / 1e9,
+                   "gather_gbs": (world - 1) * n_ch * n_sc * 8 / (float(tt[2]) * 1e-3) / 1e9,
+                   "how": "rank 0 holds [N*channels, frames] on its GPU; ncclSend/ncclRecv of contiguous row slabs "
+                          "(parallel.scatter_channels / gather_channels); device time, max over ranks; NOT part of `value`"}
+        del full_in
 
     verified = verify_against_oracle(src, dst, tb, atten, extfft, check_x, check_calls, got_last, check_ch)
     if dist is not None:
@@ -453,7 +518,8 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "out_msamples_per_s": 1e-6 * world * n_ch * n_out_total / (ms * 1e-3),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "verified": bool(verified["ok"] and verified.get("ok_all_ranks", True)), "verification": verified, "roofline": roofline, "cpu_baseline": cpu,
+                "verified": bool(verified["ok"] and verified.get("ok_all_ranks", True)), "verification": verified, "roofline": roofline, "cpu_baseline": cpu, "scatter_gather": scatter,
+                "scatter_ms": scatter["scatter_ms"] if scatter else None, "gather_ms": scatter["gather_ms"] if scatter else None,
                 "device_state_bytes": batch.device_bytes}
         print(json.dumps(line))
     if dist is not None:
