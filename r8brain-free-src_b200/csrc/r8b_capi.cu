@@ -455,7 +455,14 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
         const long long emit_in = (i == 0) ? 0 : st[i - 1].max_out_len;
         // Fusable pair: [BlockConv 2/1 with a kernel that fits M=4096 tiles] -> [FracInterp].
         if (i + 1 < st.size() && !getenv("R8BGPU_NO_FUSION")) {
-            const FusedGeom fg = fused_geometry(s, st[i + 1]);
+            FusedGeom fg = fused_geometry(s, st[i + 1]);
+            if (fg.ok && fg.up == 1) {
+                // the 1x pair exists only in the v2 kernel with the tensor-path interpolation: its bank must fit
+                const GroupBank tb = build_group_bank(st[i + 1], 8, true);
+                if (getenv("R8BGPU_FUSED_V1") || !(b->f2_flags & 4) || tb.n_groups > 192 ||
+                    fused2_smem_bytes(tb.n_groups * tb.smaxp * tb.ir, false) > kFused2SmemMax)
+                    fg.ok = false;
+            }
             if (fg.ok) {
                 d.fused_with_next = true;
                 b->dev[i + 1].fused_into_prev = true;
@@ -512,7 +519,7 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 const std::vector<double2> tt = build_tw_tab(tw);
                 if (!cuda_ok(cudaMalloc(&d.tw_tab, tt.size() * sizeof(double2)), "cudaMalloc(tw_tab)")) return nullptr;
                 if (!cuda_ok(cudaMemcpy(d.tw_tab, tt.data(), tt.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy tw_tab")) return nullptr;
-                const std::vector<double2> ctb = build_c_tab(spec, tw);
+                const std::vector<double2> ctb = build_c_tab(spec, tw, d.fgeom.up);
                 if (!cuda_ok(cudaMalloc(&d.c_tab, ctb.size() * sizeof(double2)), "cudaMalloc(c_tab)")) return nullptr;
                 if (!cuda_ok(cudaMemcpy(d.c_tab, ctb.data(), ctb.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy c_tab")) return nullptr;
             }
@@ -985,6 +992,8 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.flags = b->f2_flags;
                 p.tw_tab = d.tw_tab;
                 p.c_tab = d.c_tab;
+                p.up = d.fgeom.up;
+                p.ylen = d.fgeom.up * 4096;
                 if (!fd.bank_frag_order) p.flags &= ~4; // (the bank layout decides: see batch_create)
                 p.stage_off = (p.ir == 8 && !(p.flags & 4) && fused2_smem_bytes(p.gbank_smem_len, true) <= kFused2SmemMax &&
                                !getenv("R8BGPU_NO_STAGE")) ? fused2_stage_off(p.gbank_smem_len) : 0;

@@ -132,7 +132,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // flags: bit 0 = ping-pong token around the interpolation, bit 1 = bulk-copy input tiles
 // TC: interpolation as 8x8x4 fp64 matrix products (IRV == 8; GLOG unused)
-template <int IRV, bool PADV, int GLOG, bool TC>
+// UP: up-factor of the BlockConvolver (2: 4096-point complex inverse, 8192 stream samples per tile; 1: 2048-point inverse
+// mirroring the real-input forward transform, 4096 samples per tile -- TC only)
+template <int IRV, bool PADV, int GLOG, bool TC, int UP = 2>
 __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ FusedParams p, const __grid_constant__ SrcView src,
                                                       const __grid_constant__ DstView dst)
 {
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
     uint32_t par_in = 0, par_turn = 0;
     Tile t;
     int path = -1;
-    auto tile_src = [&](const Tile& tt) { return src.cur + (long long) tt.ch * src.cur_stride + (tt.w - src.cur_base); };
+    auto tile_src = [&](const Tile& tt) { return tile_run(src, tt); };
     if (u < n_units) {
         t = tile_of(p, u);
         path = tile_input_path(src, t);
@@ -224,21 +226,42 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
             c_load(buf, ht, z1, z2);
             if (ht == 0) ze = buf[fft_pad(slot_of<FN>(FN / 2))];
             bar_half(h);
+            if constexpr (UP == 2) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) c_pair_tab(p, buf, ht, i, z1[i], z2[i]);
-            if (ht == 0) c_pair(p, buf, FN / 2, ze, ze);
+                for (int i = 0; i < 4; i++) c_pair_tab(p, buf, ht, i, z1[i], z2[i]);
+                if (ht == 0) c_pair(p, buf, FN / 2, ze, ze);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) c1_pair_tab(p, buf, ht, i, z1[i], z2[i]);
+                if (ht == 0) c1_pair_mid(p, buf, ze);
+            }
         }
         bar_half(h);
         // D. inverse transform
-        inv_pass<16>(buf, tw2, ht);
-        __syncwarp();
-        inv_pass<256>(buf, tw2, ht);
-        bar_half(h);
-        {
-            double2 v[16];
-            inv3_load(buf, tw2, twf, ht, v);
+        if constexpr (UP == 2) {
+            inv_pass<16>(buf, tw2, ht);
+            __syncwarp();
+            inv_pass<256>(buf, tw2, ht);
             bar_half(h);
-            y_store<PADV>(buf, v, ht, t.w, p.ysh);
+            {
+                double2 v[16];
+                inv3_load(buf, tw2, twf, ht, v);
+                bar_half(h);
+                y_store<PADV>(buf, v, ht, t.w, p.ysh);
+            }
+        } else {
+            if (ht < FN / 16) {
+                inv_pass<16>(buf, tw2, ht);
+                __syncwarp();
+                inv_pass<256>(buf, tw2, ht);
+            }
+            bar_half(h);
+            {
+                double2 v[8];
+                inv1_last_load(buf, tw2, twf, ht, v);
+                bar_half(h);
+                y_store1<PADV>(buf, v, ht, t.w, p.ysh);
+            }
         }
         bar_half(h);
         // E. interpolation out of shared memory
@@ -316,11 +339,11 @@ int fused2_smem_bytes(int bank_doubles, bool staged)
 }
 int fused2_stage_off(int bank_doubles) { return 2 * (2 * FPL + 512) + ((bank_doubles + 1) & ~1); }
 
-template <int IRV, bool PADV, int GLOG, bool TC = false>
+template <int IRV, bool PADV, int GLOG, bool TC = false, int UP = 2>
 static void launch_inst2(const FusedParams& p, const SrcView& src, const DstView& dst, int grid, int smem, cudaStream_t st)
 {
-    ensure_dyn_smem<k_up2_frac2<IRV, PADV, GLOG, TC>>(227 * 1024);
-    k_up2_frac2<IRV, PADV, GLOG, TC><<<(unsigned) grid, NT2, smem, st>>>(p, src, dst);
+    ensure_dyn_smem<k_up2_frac2<IRV, PADV, GLOG, TC, UP>>(227 * 1024);
+    k_up2_frac2<IRV, PADV, GLOG, TC, UP><<<(unsigned) grid, NT2, smem, st>>>(p, src, dst);
 }
 
 // p.n_ch, p.n_tiles, p.span ... describe the call; n_sm = SMs of the device (persistent grid).
@@ -335,7 +358,10 @@ void launch_up2_frac2(const FusedParams& p, const SrcView& src, const DstView& d
 #define R8B_F2_CASE(IRV, GL)                                                              \
     if (pad) launch_inst2<IRV, true, GL>(p, src, dst, grid, smem, st);                    \
     else launch_inst2<IRV, false, GL>(p, src, dst, grid, smem, st);
-    if (p.ir == 8 && (p.flags & 4)) {
+    if (p.up == 1) { // batch_create only routes a 1x pair here when the tensor-path bank fits
+        if (pad) launch_inst2<8, true, 0, true, 1>(p, src, dst, grid, smem, st);
+        else launch_inst2<8, false, 0, true, 1>(p, src, dst, grid, smem, st);
+    } else if (p.ir == 8 && (p.flags & 4)) {
         if (pad) launch_inst2<8, true, 0, true>(p, src, dst, grid, smem, st);
         else launch_inst2<8, false, 0, true>(p, src, dst, grid, smem, st);
     } else if (p.ir == 10) {

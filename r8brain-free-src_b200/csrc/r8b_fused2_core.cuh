@@ -40,17 +40,29 @@ R8B_HD Tile tile_of(const FusedParams& p, int u)
     t.A0 = p.p_lo + (long long) ti * p.span;
     t.A1 = t.A0 + p.span;
     if (t.A1 > p.p_hi) t.A1 = p.p_hi;
-    // valid y of the tile starts at A0 - yl (even) = 2 * (first valid m); the window starts lg earlier
-    t.w = (t.A0 - p.yl) / 2 - p.lg;
+    // valid y of the tile starts at A0 - yl (even) = 2 * (first valid m) [up 2; up 1: = first valid m]; the window starts lg earlier
+    t.w = (p.up == 1 ? t.A0 - p.yl : (t.A0 - p.yl) / 2) - p.lg;
     return t;
 }
 
-// Which way the tile's 4096 input samples arrive: 0 = every sample individually (history ring, or past
-// the available input), 1 = plain loads from the caller's block, 2 = one bulk copy (16-byte aligned run).
+// Where the tile's 4096 input samples are contiguous in memory: the caller's block (first stage of a chain), or the
+// source ring when the window neither wraps nor reaches past the samples written so far (later stages).
+R8B_HD const double* tile_run(const SrcView& src, const Tile& t)
+{
+    if (t.w >= src.cur_base && t.w + FM <= src.avail) return src.cur + (long long) t.ch * src.cur_stride + (t.w - src.cur_base);
+    if (t.w >= 0 && t.w + FM <= src.avail && t.w + FM <= src.cur_base) {
+        const long long i0 = t.w & src.ring_mask;
+        if (i0 + FM <= src.ring_mask + 1) return src.ring + (long long) t.ch * src.ring_stride + i0;
+    }
+    return nullptr;
+}
+
+// Which way the samples arrive: 0 = every sample individually (history ring across a wrap, before the start, or past
+// the available input), 1 = plain loads from a contiguous run, 2 = one bulk copy (16-byte aligned run).
 R8B_HD int tile_input_path(const SrcView& src, const Tile& t)
 {
-    if (!(t.w >= src.cur_base && t.w + FM <= src.avail)) return 0;
-    const double* a = src.cur + (long long) t.ch * src.cur_stride + (t.w - src.cur_base);
+    const double* a = tile_run(src, t);
+    if (a == nullptr) return 0;
     return (reinterpret_cast<unsigned long long>(a) & 15) == 0 ? 2 : 1;
 }
 
@@ -58,7 +70,7 @@ R8B_HD int tile_input_path(const SrcView& src, const Tile& t)
 R8B_HD void gather_tile(double2 (&v)[8], const SrcView& src, const Tile& t, int path, int r)
 {
     if (path != 0) {
-        const double* __restrict__ a = src.cur + (long long) t.ch * src.cur_stride + (t.w - src.cur_base) + 2 * r;
+        const double* __restrict__ a = tile_run(src, t) + 2 * r;
         if ((reinterpret_cast<unsigned long long>(a) & 15) == 0) {
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = R8B_LDG(reinterpret_cast<const double2*>(a + 512 * j));
@@ -173,6 +185,83 @@ R8B_HD void y_store(double2* __restrict__ buf, const double2 (&v)[16], int g, lo
     }
 }
 
+// ---- up-factor 1 (BlockConvolver 1/1 -> interpolator: the tail of every decimating chain) -------------------------
+// The tile's 4096 real outputs come from a 2048-point complex INVERSE transform, the mirror of the real-input forward
+// one:  with Y[k] = X[k] H[k] (k = 0..N, Hermitian beyond),  Z'[k] = (Y[k] + conj Y[N-k]) + i W_M^-k (Y[k] - conj Y[N-k])
+// and IFFT_N(Z')[m] = y[2m] + i y[2m+1].  Per pair (k, N-k), from the forward values z1 = Z[k], z2 = Z[N-k]:
+//   x0 = 2X[k] = a + W^k b,  x1 = 2X[k+N] = a - W^k b   (a, b as in c_pair_ops);   2X[N-k] = conj x1
+//   p = x0 h0,  q = conj(x1) h1          (h0 = H[k]/2, h1 = H[N-k]/2; H = FFT(h)/M is real up to rounding)
+//   s = p + conj q,  t = i conj(W^k) (p - conj q);   Z'[k] = s + t,  Z'[N-k] = conj(s - t)
+// k = 0 pairs DC with the Nyquist bin (h1 = H[N]/2) and k = N/2 pairs with itself: both write one slot.
+R8B_HD void c1_pair_ops(double2* __restrict__ buf, int k, double2 z1, double2 z2, double2 w, double2 h0, double2 h1)
+{
+    const double2 a = make_double2(z1.x + z2.x, z1.y - z2.y);
+    const double2 b = make_double2(z1.y + z2.y, z2.x - z1.x);
+    const double2 wb = cmul<+1>(b, w);
+    const double2 x0 = make_double2(a.x + wb.x, a.y + wb.y);
+    const double2 x1c = make_double2(a.x - wb.x, wb.y - a.y); // conj(a - wb)
+    const double2 pp = cmul<+1>(x0, h0), qq = cmul<+1>(x1c, h1);
+    const double2 sm = make_double2(pp.x + qq.x, pp.y - qq.y);
+    const double2 df = make_double2(pp.x - qq.x, pp.y + qq.y);
+    const double2 cd = cmul<-1>(df, w);                        // conj(W^k) (p - conj q)
+    const double2 tt = make_double2(-cd.y, cd.x);              // times i
+    const int s0 = slot_of<FN>(k), s1 = slot_of<FN>((FN - k) & (FN - 1));
+    buf[fft_pad(s0)] = make_double2(sm.x + tt.x, sm.y + tt.y);
+    if (s1 != s0) buf[fft_pad(s1)] = make_double2(sm.x - tt.x, tt.y - sm.y);
+}
+
+R8B_HD void c1_pair_tab(const FusedParams& p, double2* __restrict__ buf, int ht, int u, double2 z1, double2 z2)
+{
+    const double2* __restrict__ ct = p.c_tab + (u * 3) * HT + ht;
+    c1_pair_ops(buf, c_freq(ht, u), z1, z2, R8B_LDG(ct), R8B_LDG(ct + HT), R8B_LDG(ct + 2 * HT));
+}
+
+R8B_HD void c1_pair_mid(const FusedParams& p, double2* __restrict__ buf, double2 ze)
+{
+    const double2* __restrict__ ct = p.c_tab + 12 * HT;
+    c1_pair_ops(buf, FN / 2, ze, ze, R8B_LDG(ct), R8B_LDG(ct + 1), R8B_LDG(ct + 2));
+}
+
+// inverse, last pass of the 2048-point transform (radix 8, D = 256): mirror of fwd_pass1_r8
+R8B_HD void inv1_last_load(const double2* __restrict__ buf, const double2* __restrict__ twc, const double2* __restrict__ twf, int r,
+                           double2 (&v)[8])
+{
+    const double2 w1 = tw_pair(twc, twf, r, 2), w2 = tw_pair(twc, twf, r, 4), w4 = tw_pair(twc, twf, r, 8);
+    const double2 w3 = cprod(w1, w2);
+    v[0] = buf[fft_pad(r)];
+    v[1] = cmul<-1>(buf[fft_pad(r + 1 * 256)], w1);
+    v[2] = cmul<-1>(buf[fft_pad(r + 2 * 256)], w2);
+    v[3] = cmul<-1>(buf[fft_pad(r + 3 * 256)], w3);
+    v[4] = cmul<-1>(buf[fft_pad(r + 4 * 256)], w4);
+    v[5] = cmul<-1>(buf[fft_pad(r + 5 * 256)], cprod(w1, w4));
+    v[6] = cmul<-1>(buf[fft_pad(r + 6 * 256)], cprod(w2, w4));
+    v[7] = cmul<-1>(buf[fft_pad(r + 7 * 256)], cprod(w3, w4));
+    Network<8, -1>::run(v);
+}
+
+// element m = r + 256 j of the result is y[2m] + i y[2m+1], local positions of the 1x stream (position w + index)
+template <bool PADV>
+R8B_HD void y_store1(double2* __restrict__ buf, const double2 (&v)[8], int r, long long w, int ysh)
+{
+    double* yb = reinterpret_cast<double*>(buf);
+    const bool head = w < 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int m = r + j * 256;
+        double2 x = v[bitrev<8>(j)];
+        if (head) { // the reference's interpolator starts from silence
+            if (w + 2 * m < 0) x.x = 0.0;
+            if (w + 2 * m + 1 < 0) x.y = 0.0;
+        }
+        if (!PADV) {
+            reinterpret_cast<double2*>(yb)[m] = x;
+        } else {
+            yb[ylay(2 * m, ysh)] = x.x;
+            yb[ylay(2 * m + 1, ysh)] = x.y;
+        }
+    }
+}
+
 // Tile-level bookkeeping of the interpolation, by ONE thread while the transforms run: everything the
 // per-task code needs afterwards is 32-bit and relative to the tile.
 //   s_i[0] outputs of the tile, [1] last (shifted) stepping cycle, [2] output index of (cycle 0, phase 0)
@@ -188,7 +277,7 @@ R8B_HD void interp_prepare(const FusedParams& p, const DstView& dst, const Tile&
     s_i[0] = jb > ja ? (int) (jb - ja) : 0;
     s_i[1] = (int) (c_last - c_first);
     s_i[2] = (int) (c_first * p.out_step - ja);
-    s_i[3] = (int) (c_first * p.in_step - p.fll - 2 * t.w);
+    s_i[3] = (int) (c_first * p.in_step - p.fll - (p.up == 1 ? 1 : 2) * t.w);
     *s_op = dst.ptr + (long long) t.ch * dst.stride + ((ja - dst.base) & dst.mask);
 }
 
@@ -358,7 +447,7 @@ R8B_HD int mma_a_index(const FusedParams& p, const MmaTile& mt, const MmaUnit& u
     if (c > mt.c_cnt) c = mt.c_cnt;          // rows past the last cycle compute something valid and never store
     int li = c * p.in_step + goff + mt.wbase;
     if (li < 0) li = 0;
-    if (li > 2 * FM - p.smaxp) li = 2 * FM - p.smaxp;
+    if (li > p.ylen - p.smaxp) li = p.ylen - p.smaxp;
     return li + (lane & 3);
 }
 

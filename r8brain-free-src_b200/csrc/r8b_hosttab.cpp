@@ -90,9 +90,29 @@ std::vector<double2> build_tw_tab(const std::vector<double2>& tw)
     return tt;
 }
 
-std::vector<double2> build_c_tab(const std::vector<double2>& spec, const std::vector<double2>& tw)
+std::vector<double2> build_c_tab(const std::vector<double2>& spec, const std::vector<double2>& tw, int up)
 {
     using namespace f2;
+    if (up == 1) {
+        // H[k]/2 for k = 0..N from the slot-ordered table of FFT(h)/M (the halving is exact)
+        auto hk = [&](int k) {
+            const double2 v = spec[(size_t) slot_of<FM>(k)];
+            return make_double2(0.5 * v.x, 0.5 * v.y);
+        };
+        std::vector<double2> ct((size_t) 4 * 3 * HT + 3);
+        for (int u = 0; u < 4; u++)
+            for (int ht = 0; ht < HT; ht++) {
+                const int k = c_freq(ht, u);
+                double2* e = &ct[(size_t) (u * 3) * HT + ht];
+                e[0] = tw[(size_t) k];
+                e[HT] = hk(k);
+                e[2 * HT] = hk(FN - k); // k = 0: the Nyquist bin
+            }
+        ct[(size_t) 12 * HT] = tw[(size_t) (FN / 2)];
+        ct[(size_t) 12 * HT + 1] = hk(FN / 2);
+        ct[(size_t) 12 * HT + 2] = hk(FN / 2);
+        return ct;
+    }
     std::vector<double2> ct((size_t) 4 * 5 * HT);
     for (int u = 0; u < 4; u++)
         for (int ht = 0; ht < HT; ht++) {
@@ -110,17 +130,20 @@ std::vector<double2> build_c_tab(const std::vector<double2>& spec, const std::ve
 FusedGeom fused_geometry(const StageDesc& s, const StageDesc& f)
 {
     FusedGeom g;
-    if (!(s.kind == ST_BLOCKCONV && s.up == 2 && s.down == 1 && !s.block_exact &&
-          (f.kind == ST_FRAC_WHOLE || f.kind == ST_FRAC_POLY)))
+    if (!(s.kind == ST_BLOCKCONV && (s.up == 2 || s.up == 1) && s.down == 1 && !s.block_exact &&
+          (f.kind == ST_FRAC_WHOLE || (f.kind == ST_FRAC_POLY && s.up == 2))))
         return g;
-    const int lg = (s.lp.half_len + 1) / 2;
+    g.up = s.up;
+    // half support of the filter as seen from one tile sample: polyphase branches for up 2 (input-rate samples)
+    const int lg = s.up == 2 ? (s.lp.half_len + 1) / 2 : s.lp.half_len;
     const int flen = f.bank.filter_len, fll = flen / 2 - 1;
     int dmax = 0;
     if (f.kind == ST_FRAC_WHOLE)
         dmax = (int) (((long long) 9 * f.in_step + f.out_step - 1) / f.out_step) + 1; // up to 10 phases per group
     const int yl = (fll + 2) & ~1;
     const int yr = (dmax + flen - yl + 2 + 1) & ~1;
-    const int smax = (2 * (4096 - 2 * lg) - yl - yr) & ~1;
+    // stream positions a tile can own: the valid part of its (up * 4096)-sample window minus the interpolation margins
+    const int smax = (s.up * (4096 - 2 * lg) - yl - yr) & ~1;
     if (!(smax >= 1024 && (f.kind == ST_FRAC_POLY || f.in_step < smax / 2))) return g;
     g.ok = true;
     g.lg = lg;
@@ -210,8 +233,9 @@ void fused2_tiles(FusedParams& p, const FusedGeom& g, int cur_parity)
     // One tile per half-CTA, no pairing.  Spans are multiples of 4 so that every tile's FFT window starts on the
     // same parity of the input index, and p_lo gives way by one sample pair where that makes the windows start
     // 16-byte aligned in the caller's block.
-    const long long w0 = (p.p_lo - g.yl) / 2 - g.lg;
-    if (cur_parity >= 0 && (((w0 & 1) != 0) != (cur_parity != 0)) && p.p_lo >= 2) p.p_lo -= 2;
+    const long long w0 = (g.up == 1 ? p.p_lo - g.yl : (p.p_lo - g.yl) / 2) - g.lg;
+    const int back = g.up == 1 ? 1 : 2; // stream positions per input sample
+    if (cur_parity >= 0 && (((w0 & 1) != 0) != (cur_parity != 0)) && p.p_lo >= back) p.p_lo -= back;
     const long long range = p.p_hi - p.p_lo, smax = g.span_max & ~3;
     const long long nt = (range + smax - 1) / smax;
     p.n_tiles = (int) nt;

@@ -19,13 +19,14 @@ void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec
 
 // [q][r] twiddle tables of the fused kernels: 256 entries W_256^(r q), then 256 entries W_4096^(r q)
 std::vector<double2> build_tw_tab(const std::vector<double2>& tw4096);
-// phase C operands of the v2 fused kernel in thread order (FusedParams::c_tab)
-std::vector<double2> build_c_tab(const std::vector<double2>& spec_slots4096, const std::vector<double2>& tw4096);
+// phase C operands of the v2 fused kernel in thread order (FusedParams::c_tab); up = 1: the layout c1_pair_tab() reads
+std::vector<double2> build_c_tab(const std::vector<double2>& spec_slots4096, const std::vector<double2>& tw4096, int up = 2);
 
 // "2x BlockConvolver -> FracInterpolator" pair: margins and span of the M = 4096 tiles
 struct FusedGeom {
     bool ok = false;
     int lg = 0, yl = 0, yr = 0, span_max = 0, ysh = 31;
+    int up = 2; // up-factor of the BlockConvolver: 2, or 1 (v2 kernel with the tensor-path interpolation only)
 };
 FusedGeom fused_geometry(const StageDesc& bc, const StageDesc& frac);
 

@@ -89,7 +89,7 @@ void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, con
         const Tile t = tile_of(p, u);
         const int path = tile_input_path(src, t);
         if (path == 2) // the bulk copy
-            memcpy(buf.data() + fft_pad(FN), src.cur + (long long) t.ch * src.cur_stride + (t.w - src.cur_base), FM * sizeof(double));
+            memcpy(buf.data() + fft_pad(FN), tile_run(src, t), FM * sizeof(double));
         for (int ht = 0; ht < HT; ht++) {
             double2 v[8];
             if (path == 2) {
@@ -115,10 +115,31 @@ void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, con
                 }
             }
             const double2 ze = buf[(size_t) fft_pad(slot_of<FN>(FN / 2))];
-            for (int ht = 0; ht < HT; ht++)
-                for (int i = 0; i < 4; i++) c_pair_tab(p, buf.data(), ht, i, z1[(size_t) ht * 4 + i], z2[(size_t) ht * 4 + i]);
-            c_pair(p, buf.data(), FN / 2, ze, ze);
+            if (p.up == 1) {
+                for (int ht = 0; ht < HT; ht++)
+                    for (int i = 0; i < 4; i++) c1_pair_tab(p, buf.data(), ht, i, z1[(size_t) ht * 4 + i], z2[(size_t) ht * 4 + i]);
+                c1_pair_mid(p, buf.data(), ze);
+            } else {
+                for (int ht = 0; ht < HT; ht++)
+                    for (int i = 0; i < 4; i++) c_pair_tab(p, buf.data(), ht, i, z1[(size_t) ht * 4 + i], z2[(size_t) ht * 4 + i]);
+                c_pair(p, buf.data(), FN / 2, ze, ze);
+            }
         }
+        if (p.up == 1) {
+            for (int ht = 0; ht < FN / 16; ht++) inv_pass<16>(buf.data(), tw2, ht);
+            for (int ht = 0; ht < FN / 16; ht++) inv_pass<256>(buf.data(), tw2, ht);
+            std::vector<double2> v((size_t) HT * 8);
+            for (int ht = 0; ht < HT; ht++) {
+                double2 a[8];
+                inv1_last_load(buf.data(), tw2, twf, ht, a);
+                for (int i = 0; i < 8; i++) v[(size_t) ht * 8 + i] = a[i];
+            }
+            for (int ht = 0; ht < HT; ht++) {
+                double2 a[8];
+                for (int i = 0; i < 8; i++) a[i] = v[(size_t) ht * 8 + i];
+                y_store1<PADV>(buf.data(), a, ht, t.w, p.ysh);
+            }
+        } else {
         for (int ht = 0; ht < HT; ht++) inv_pass<16>(buf.data(), tw2, ht);
         for (int ht = 0; ht < HT; ht++) inv_pass<256>(buf.data(), tw2, ht);
         {
@@ -133,6 +154,7 @@ void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, con
                 for (int i = 0; i < 16; i++) a[i] = v[(size_t) ht * 16 + i];
                 y_store<PADV>(buf.data(), a, ht, t.w, p.ysh);
             }
+        }
         }
         if (s_i[0] > 0 && E.tc) {
             if constexpr (IR == 8) interp_tc<PADV>(p, dst, t, reinterpret_cast<const double*>(buf.data()), sbank.data(), s_goff.data(), s_i, s_o);
@@ -181,11 +203,11 @@ void* f2emul_create(double src, double dst, int max_in_len, double tb, double at
         return nullptr;
     }
     E->sched.init(&E->plan);
-    E->tc = glog_force == 8;
+    E->tc = glog_force == 8 || E->fg.up == 1;
     E->B = build_group_bank(E->plan.stages[1], E->tc ? 8 : choose_group_ir(E->plan.stages[1]), E->tc);
     build_spectrum(E->plan.stages[0], 12, E->spec, E->tw, nullptr);
     E->tw_tab = build_tw_tab(E->tw);
-    E->c_tab = build_c_tab(E->spec, E->tw);
+    E->c_tab = build_c_tab(E->spec, E->tw, E->fg.up);
     E->ring.assign((size_t) 1 << 22, 0.0);
     E->ring_mask = ((long long) 1 << 22) - 1;
     E->glog_force = E->tc ? -1 : glog_force;
@@ -214,6 +236,8 @@ int f2emul_process(void* h, const double* x, int l, double* out, int out_cap)
         p.spec = E.spec.data();
         p.tw = E.tw.data();
         p.c_tab = E.c_tab.data();
+        p.up = E.fg.up;
+        p.ylen = E.fg.up * 4096;
         p.gbank = E.B.gb.data();
         p.goff = E.B.go.data();
         p.smaxp = E.B.smaxp;

@@ -83,6 +83,15 @@ def test_tensor_path_interpolation(emul, src, dst, lens):
     _run(emul, src, dst, max(lens), lens, glog=8)
 
 
+@pytest.mark.parametrize("src,dst,lens,atten", [(96000.0, 44100.0, [8192, 8192, 5, 0, 4099, 8191], 180.15),
+                                                (48000.0, 22050.0, [4096] * 4, 206.91),
+                                                (100000.0, 44100.0, [8192, 8192], 136.45)])
+def test_up1_pair_blockconv_to_interpolator(emul, src, dst, lens, atten):
+    """BlockConvolver 1/1 -> whole-stepping interpolator (the tail of the decimating chains): 2048-point inverse
+    transform mirroring the real-input forward one, tensor-path interpolation over a 4096-sample tile."""
+    _run(emul, src, dst, max(lens), lens, glog=8, atten=atten)
+
+
 def test_ragged_blocks_history_ring_and_misaligned_rows(emul):
     # odd lengths shift the block base parity (plain-load path), tiny and empty blocks reach into the history ring
     _run(emul, 44100.0, 96000.0, 8192, [1, 0, 4097, 777, 8192, 3, 8191, 5000])
