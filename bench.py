@@ -39,6 +39,7 @@ WORKLOADS = {
     "cfg5_512ch_48000_47999_r24": (48000.0, 47999.0, 180.15, 2.0, 0, 512),
     "cfg4_128ch_44100_2822400_r24_extfft": (44100.0, 2822400.0, 180.15, 2.0, 1, 128),
     "cfg3b_1024ch_192000_44100_r24": (192000.0, 44100.0, 180.15, 2.0, 0, 1024),
+    "cfg3c_1024ch_2822400_44100_r24": (2822400.0, 44100.0, 180.15, 2.0, 0, 1024),
 }
 # algorithmic flops per input sample (real-FFT 2.5 N log2 N per block + interpolation / half-band MACs)
 FLOPS_PER_IN_SAMPLE = {"cfg2_1024ch_44100_96000_r24": 241.0, "cfg3_1024ch_48000_44100_r24": 188.0,

@@ -115,6 +115,9 @@ struct StageDev {
     cudaEvent_t ft_ev[2] = {nullptr, nullptr};
     int ft_cur = 0;
     int casc_len = 0; // >= 2 on the first stage of a run of HBUP stages executed by k_hbup_cascade
+    int down_casc_len = 0; // >= 2 on the first stage of a run of HBDOWN stages executed by k_hbdown_cascade
+    HbDownCascParams down_casc; // its tile plan (taps, halos, shared-memory layout)
+    int down_casc_smem = 0;
     // v2 fused kernel (r8b_fused2.cu): [q][r] twiddle tables for the bulk copy; on the BLOCKCONV stage
     double2* tw_tab = nullptr;
     double2* c_tab = nullptr;   // v2 fused kernel: phase C operands in thread order
@@ -481,10 +484,31 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 for (size_t k = 1; k < c; k++) b->dev[i + k].fused_into_prev = true;
             }
         }
+        long long extra_history = 0;
+        if (s.kind == ST_HBDOWN && !d.fused_into_prev && !getenv("R8BGPU_NO_FUSION")) {
+            size_t c = 1;
+            while (i + c < st.size() && st[i + c].kind == ST_HBDOWN && c < 6) c++;
+            if (c >= 2) {
+                HbDownCascParams& cp = d.down_casc;
+                memset(&cp, 0, sizeof cp);
+                cp.n_stages = (int) c;
+                for (size_t k = 0; k < c; k++) {
+                    cp.ntaps[k] = st[i + k].hb_taps;
+                    for (int j = 0; j < st[i + k].hb_taps; j++) cp.taps[k][j] = st[i + k].hb[(size_t) j];
+                }
+                d.down_casc_smem = hbdown_cascade_plan(cp, 100 * 1024 / 8); // two CTAs per SM
+                if (d.down_casc_smem > 0) {
+                    d.down_casc_len = (int) c;
+                    for (size_t k = 1; k < c; k++) b->dev[i + k].fused_into_prev = true;
+                    // the cascade recomputes intermediate samples of earlier calls from the source: keep its whole reach
+                    extra_history = 2LL * cp.back[0] + (2LL << c) + 64;
+                }
+            }
+        }
         if (d.fused_into_prev) {
             d.ring_cap = 0; // the link stream lives only in shared memory
         } else {
-            d.ring_cap = next_pow2((long long) s.src_history + emit_in + 64);
+            d.ring_cap = next_pow2(std::max<long long>(s.src_history, extra_history) + emit_in + 64);
             const size_t ring_bytes = (size_t) d.ring_cap * (size_t) n_channels * sizeof(double);
             if (!cuda_ok(cudaMalloc(&d.ring, ring_bytes), "batch_create: cudaMalloc(ring)")) return nullptr;
             b->dev_bytes += ring_bytes;
@@ -718,6 +742,9 @@ int r8bgpu_batch_stage_kernel(const r8bgpu_batch* b, int stage, char* name, int 
     } else if (d.fused_with_next) {
         nm = d.f2_ok ? "k_up2_frac2" : "k_up2_frac";
         span = 2;
+    } else if (d.down_casc_len >= 2) {
+        nm = "k_hbdown_cascade";
+        span = d.down_casc_len;
     } else if (d.casc_len >= 2) {
         nm = "k_hbup_cascade";
         span = d.casc_len;
@@ -816,7 +843,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
         const StageDev& d = b->dev[i];
         if (d.fused_into_prev) continue; // handled together with the previous stage
         const bool fused = d.fused_with_next;
-        const size_t last = fused ? i + 1 : (d.casc_len >= 2 ? i + (size_t) d.casc_len - 1 : i); // stage whose output this launch produces
+        const size_t last = fused ? i + 1 : (d.casc_len >= 2 ? i + (size_t) d.casc_len - 1 : d.down_casc_len >= 2 ? i + (size_t) d.down_casc_len - 1 : i); // stage whose output this launch produces
         if (b->calls[last].e1 <= b->calls[last].e0) continue;
         SrcView src;
         src.ring = d.ring + (long long) ch0 * d.ring_cap;
@@ -850,7 +877,14 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             cudaEventCreate(&ev.b);
             cudaEventRecord(ev.a, st);
         }
-        if (d.casc_len >= 2) {
+        if (d.down_casc_len >= 2) {
+            HbDownCascParams p = d.down_casc;
+            p.e0 = b->calls[last].e0;
+            p.e1 = b->calls[last].e1;
+            p.n_tiles = (int) ((p.e1 - p.e0 + p.w - 1) / p.w);
+            launch_hbdown_cascade(p, d.down_casc_smem, src, dst, nch, st);
+            b->launches++;
+        } else if (d.casc_len >= 2) {
             const int cl = d.casc_len;
             HbCascadeParams p;
             memset(&p, 0, sizeof p);

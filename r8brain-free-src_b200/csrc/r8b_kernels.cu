@@ -367,6 +367,108 @@ void launch_hbdown(const HbParams& p, const SrcView& src, const DstView& dst, in
 }
 
 // ------------------------------------------------------------------------------------------
+// k_hbdown_cascade -- a run of half-band decimators (CDSPHBDownsampler.h:137-239, chained by CDSPResampler.h:337-346,
+// 372-391) in ONE launch.  A CTA owns `w` consecutive outputs of the LAST stage of one channel; the source samples they
+// depend on (w * 2^n plus the halo the taps reach through all stages) are read once, every intermediate rate is computed
+// into shared memory, only the last stage's outputs leave.  Each stream is kept as two arrays, samples of even and of odd
+// absolute index: stage arithmetic  out[m] = x[2m] + sum_k f[k] (x[2m+1+2k] + x[2m-1-2k])  then reads consecutive words
+// for consecutive m (E[m] and O[m+k], O[m-1-k]), the layout k_hbdown uses for one stage.  Stream s covers absolute
+// indices [lo_s, hi_s):  lo_s = 2 lo_{s+1} - (2 T_s - 1),  hi_s = 2 hi_{s+1} + 2 T_s - 2.  Outputs a stage has not yet
+// "emitted" are never needed: an output is emitted exactly when its whole upward reach has arrived (r8b_plan.h), so
+// every halo read lies below the source's `avail`; indices below zero read the zero history.  Same summation order per
+// output as k_hbdown: centre sample, then taps k = 0..T-1.
+constexpr int HBDC_NT = 256;
+__global__ void __launch_bounds__(HBDC_NT) k_hbdown_cascade(const __grid_constant__ HbDownCascParams p, const __grid_constant__ SrcView src,
+                                                            const __grid_constant__ DstView dst)
+{
+    extern __shared__ double hsm[];
+    const int n = p.n_stages, tid = threadIdx.x;
+    const int ch = blockIdx.x / p.n_tiles, ti = blockIdx.x - ch * p.n_tiles;
+    const long long m0 = p.e0 + (long long) ti * p.w;
+    long long m1 = m0 + p.w;
+    if (m1 > p.e1) m1 = p.e1;
+    if (m1 <= m0) return;
+    // stream 0: [lo, hi) = [2^n m0 - back[0], 2^n (m1 - 1) + back[0] + 1)
+    {
+        const long long lo = (m0 << n) - p.back[0], hi = ((m1 - 1) << n) + p.back[0] + 1;
+        double* E = hsm + p.boff[0];
+        double* O = E + p.cap[0];
+        // element with absolute index a lives at E[(a - lo_e) / 2] (a even) or O[(a - lo_o) / 2] (a odd), lo_e / lo_o the
+        // first even / odd index >= lo
+        const long long lo_e = lo + (lo & 1), lo_o = lo + 1 - (lo & 1);
+        const int cnt = (int) (hi - lo);
+        const bool fast = lo >= src.cur_base && hi <= src.avail;
+        const double* __restrict__ a = fast ? src.cur + (long long) ch * src.cur_stride + (lo - src.cur_base) : nullptr;
+        for (int i = tid; i < cnt; i += HBDC_NT) {
+            const long long idx = lo + i;
+            const double x = fast ? __ldg(a + i) : src_read(src, ch, idx);
+            if (idx & 1) O[(idx - lo_o) >> 1] = x;
+            else E[(idx - lo_e) >> 1] = x;
+        }
+    }
+    __syncthreads();
+    for (int s = 0; s < n; s++) {
+        const int T = p.ntaps[s], sh = n - s;
+        // input stream s and output stream s + 1 ranges
+        const long long ilo = (m0 << sh) - p.back[s];
+        const long long olo = (m0 << (sh - 1)) - p.back[s + 1], ohi = ((m1 - 1) << (sh - 1)) + p.back[s + 1] + 1;
+        const double* __restrict__ Ei = hsm + p.boff[s];
+        const double* __restrict__ Oi = Ei + p.cap[s];
+        const long long ilo_e = ilo + (ilo & 1), ilo_o = ilo + 1 - (ilo & 1);
+        const bool last = (s + 1 == n);
+        double* Eo = last ? nullptr : hsm + p.boff[s + 1];
+        double* Oo = last ? nullptr : Eo + p.cap[s + 1];
+        const long long olo_e = olo + (olo & 1), olo_o = olo + 1 - (olo & 1);
+        const int cnt = (int) (ohi - olo);
+        const double* __restrict__ f = p.taps[s];
+        for (int i = tid; i < cnt; i += HBDC_NT) {
+            const long long m = olo + i;
+            // x[2m] = E[(2m - ilo_e)/2]; x[2m+1+2k] = O[(2m + 1 + 2k - ilo_o)/2]; x[2m-1-2k] = O[(2m - 1 - 2k - ilo_o)/2]
+            const int ie = (int) ((2 * m - ilo_e) >> 1), io = (int) ((2 * m + 1 - ilo_o) >> 1);
+            double acc = Ei[ie];
+            for (int k = 0; k < T; k++) acc = fma(f[k], Oi[io + k] + Oi[io - 1 - k], acc);
+            if (m < 0) acc = 0.0; // a stage's stream starts at index 0: the next stage sees silence before it
+            if (last) dst_write(dst, ch, m, acc);
+            else if (m & 1) Oo[(m - olo_o) >> 1] = acc;
+            else Eo[(m - olo_e) >> 1] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+int hbdown_cascade_plan(HbDownCascParams& p, int smem_budget_doubles)
+{
+    const int n = p.n_stages;
+    p.back[n] = 0;
+    for (int s = n - 1; s >= 0; s--) p.back[s] = 2 * p.back[s + 1] + 2 * p.ntaps[s] - 1;
+    // widest tile whose buffers fit: stream s holds (w - 1) * 2^(n-s) + 2 back[s] + 1 samples, split in two halves
+    int best = 0;
+    for (int w = 8; w <= 1024; w *= 2) {
+        long long tot = 0;
+        for (int s = 0; s < n; s++) tot += 2 * ((((long long) (w - 1) << (n - s)) + 2 * p.back[s] + 1) / 2 + 2);
+        if (tot <= smem_budget_doubles) best = w;
+    }
+    if (best == 0) return 0;
+    p.w = best;
+    int off = 0;
+    for (int s = 0; s < n; s++) {
+        p.cap[s] = (int) ((((long long) (best - 1) << (n - s)) + 2 * p.back[s] + 1) / 2 + 2);
+        p.boff[s] = off;
+        off += 2 * p.cap[s];
+    }
+    p.boff[n] = off;
+    p.cap[n] = 0;
+    return off * (int) sizeof(double);
+}
+
+void launch_hbdown_cascade(const HbDownCascParams& p, int smem_bytes, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
+{
+    if (p.e1 <= p.e0 || n_ch <= 0 || p.n_tiles <= 0) return;
+    ensure_dyn_smem<k_hbdown_cascade>(smem_bytes > 48 * 1024 ? smem_bytes : 48 * 1024);
+    k_hbdown_cascade<<<(unsigned) ((long long) p.n_tiles * n_ch), HBDC_NT, smem_bytes, st>>>(p, src, dst);
+}
+
+// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_save_tail(const double* __restrict__ cur, long long cur_stride,
                                                    long long cur_base, long long n0, long long n1,
                                                    double* __restrict__ ring, long long ring_stride,

@@ -86,6 +86,22 @@ struct HbParams {
     double taps[14];
 };
 
+// Fused chain of up to 6 half-band 2x DOWNsamplers (k_hbdown_cascade): every intermediate rate lives in shared memory.
+// Stream s is the input of stage s (stream 0 = the cascade's source, stream n_stages = its output).
+struct HbDownCascParams {
+    int n_stages;
+    int ntaps[6];
+    double taps[6][14];
+    long long e0, e1;      // output indices of the LAST stage to write
+    int w;                 // final outputs per tile
+    int n_tiles;
+    int back[7];           // stream-s samples needed below 2^(n-s) * m for final output m (back[n] = 0)
+    int boff[7];           // offsets (doubles) of the per-stream buffers in dynamic shared memory: even half, then odd half
+    int cap[7];            // doubles per half of stream s's buffer
+};
+int hbdown_cascade_plan(HbDownCascParams& p, int smem_budget_doubles); // fills w, back, boff, cap; returns smem bytes (0: does not fit)
+void launch_hbdown_cascade(const HbDownCascParams& p, int smem_bytes, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st);
+
 // Fused chain of up to 6 half-band 2x upsamplers (k_hbup_cascade).
 struct HbCascadeParams {
     int n_stages;

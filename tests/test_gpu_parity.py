@@ -82,6 +82,27 @@ def test_hbdown_cascade(pkg, ref):
     check(ys, yr)
 
 
+def test_decimating_chains_are_fused(pkg, ref):
+    """The five half-band decimators of 2822400 -> 44100 run as ONE kernel (k_hbdown_cascade) followed by the block
+    convolver: two launches per call (+ the history copy); 192000 -> 44100 runs its 1x BlockConvolver and interpolator
+    in the fused kernel.  Ragged calls reach across call boundaries into the cascade's recomputed history."""
+    plan = pkg.Plan(2822400.0, 44100.0, 65536, 2.0, pkg.ATTEN_24)
+    batch = pkg.Batch(plan, 2, 0)
+    names = batch.stage_kernels()
+    assert names[0] == ("k_hbdown_cascade", 5) and all(n == ("(fused)", 0) for n in names[1:5]), names
+    x = ou.white_noise(2, 65536, 3)
+    batch.process_host(x)
+    l0 = batch.kernel_launches
+    batch.process_host(x)
+    assert batch.kernel_launches - l0 == 3, batch.kernel_launches - l0  # cascade, block convolver, history copy
+    b2 = pkg.Batch(pkg.Plan(192000.0, 44100.0, 8192, 2.0, pkg.ATTEN_24), 2, 0)
+    assert [n[0] for n in b2.stage_kernels()] == ["k_hbdown", "k_up2_frac2", "(fused)"]
+    ys, yr = run_both(pkg, ref, 2822400.0, 44100.0, [65536, 1000, 65536, 7, 0, 33333, 65536, 65536, 65536], n_ch=3, max_in=65536)
+    check(ys, yr)
+    ys, yr = run_both(pkg, ref, 705600.0, 44100.0, [30000] * 6, n_ch=2, max_in=30000)
+    check(ys, yr)
+
+
 def test_full_block_size(pkg, ref):
     # BASELINE block size: 65536-sample calls, counts 138963, 142664, 142663 ...
     ys, yr = run_both(pkg, ref, 44100.0, 96000.0, [65536] * 3, n_ch=2)
