@@ -523,8 +523,16 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
             if (s.block_exact) { // tiles == the reference's own blocks
                 d.lg = s.ref_prev_len - s.lp.half_len;
                 d.fft_log2 = s.lp.block_len_bits + 1;
-                // M = 8192 exists for 1x stages (single buffer); 2x stages stop at 4096
-                if (d.fft_log2 < 10 || d.fft_log2 > (up_eff == 1 ? 13 : 12)) d.fft_log2 = -1;
+                // the tile IS the reference's block (2 << BlockLenBits): 64 .. 8192 points for 1x stages (short kernels run on
+                // plain radix-2 transforms); 2x stages have tiles of 1024 .. 4096
+                const int lo = up_eff == 1 ? 6 : 10, hi = up_eff == 1 ? 13 : 12;
+                if (d.fft_log2 < lo || d.fft_log2 > hi) {
+                    char msg[200];
+                    snprintf(msg, sizeof msg, "batch_create: reference-exact decimation needs a %d-point block transform; "
+                             "this build has %d..%d points for such stages", 1 << d.fft_log2, 1 << lo, 1 << hi);
+                    set_err(msg);
+                    return nullptr;
+                }
             }
             if (d.fused_with_next) d.fft_log2 = 12; // the fused kernel is built for M = 4096
             if (d.fft_log2 < 0) {

@@ -152,44 +152,89 @@ __device__ __forceinline__ void fft_pass_inverse(double2* __restrict__ s,
     }
 }
 
+// Short transforms (M = 64 .. 512): plain radix-2 stages, spectrum in bit-reversed order.  They only serve the
+// reference-exact power-of-two decimation of SHORT low-pass kernels, whose tiles must coincide with the reference's own
+// small blocks (2 << BlockLenBits, CDSPFIRFilter.h:461); a few thousand points per tile -- throughput is not a concern.
+template <int M, int NT, int DIR>
+__device__ __forceinline__ void fft_small(double2* s, const double2* tw, int tid)
+{
+    if (DIR > 0) {
+#pragma unroll 1
+        for (int len = M; len >= 2; len >>= 1) {
+            const int half = len >> 1, step = M / len;
+            for (int b = tid; b < M / 2; b += NT) {
+                const int blk = b / half, r = b - blk * half;
+                const int i0 = blk * len + r, i1 = i0 + half;
+                const double2 a = s[fft_pad(i0)], c = s[fft_pad(i1)];
+                s[fft_pad(i0)] = make_double2(a.x + c.x, a.y + c.y);
+                const double2 d = make_double2(a.x - c.x, a.y - c.y);
+                s[fft_pad(i1)] = r == 0 ? d : cmul<+1>(d, __ldg(&tw[r * step]));
+            }
+            __syncthreads();
+        }
+    } else {
+#pragma unroll 1
+        for (int len = 2; len <= M; len <<= 1) {
+            const int half = len >> 1, step = M / len;
+            for (int b = tid; b < M / 2; b += NT) {
+                const int blk = b / half, r = b - blk * half;
+                const int i0 = blk * len + r, i1 = i0 + half;
+                const double2 a = s[fft_pad(i0)];
+                double2 c = s[fft_pad(i1)];
+                if (r != 0) c = cmul<-1>(c, __ldg(&tw[r * step]));
+                s[fft_pad(i0)] = make_double2(a.x + c.x, a.y + c.y);
+                s[fft_pad(i1)] = make_double2(a.x - c.x, a.y - c.y);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // Full transforms.  M = R1 * 256.  Callers must __syncthreads() before (data ready) and the
 // functions end with a __syncthreads().
 template <int M, int NT>
 __device__ __forceinline__ void fft_forward(double2* s, const double2* tw, int tid)
 {
-    if constexpr (M == 8192) { // 2 * 16 * 16 * 16
-        fft_pass_forward<M, M, 2, NT>(s, tw, tid);
-        __syncthreads();
-        fft_pass_forward<M, 4096, 16, NT>(s, tw, tid);
-        __syncthreads();
+    if constexpr (M <= 512) {
+        fft_small<M, NT, +1>(s, tw, tid);
     } else {
-        constexpr int R1 = M / 256;
-        fft_pass_forward<M, M, R1, NT>(s, tw, tid);
+        if constexpr (M == 8192) { // 2 * 16 * 16 * 16
+            fft_pass_forward<M, M, 2, NT>(s, tw, tid);
+            __syncthreads();
+            fft_pass_forward<M, 4096, 16, NT>(s, tw, tid);
+            __syncthreads();
+        } else {
+            constexpr int R1 = M / 256;
+            fft_pass_forward<M, M, R1, NT>(s, tw, tid);
+            __syncthreads();
+        }
+        fft_pass_forward<M, 256, 16, NT>(s, tw, tid);
+        __syncthreads();
+        fft_pass_forward<M, 16, 16, NT>(s, tw, tid);
         __syncthreads();
     }
-    fft_pass_forward<M, 256, 16, NT>(s, tw, tid);
-    __syncthreads();
-    fft_pass_forward<M, 16, 16, NT>(s, tw, tid);
-    __syncthreads();
 }
 
 template <int M, int NT>
 __device__ __forceinline__ void fft_inverse(double2* s, const double2* tw, int tid)
 {
-    constexpr int R1 = (M == 8192) ? 2 : M / 256;
-    (void) R1;
-    fft_pass_inverse<M, 16, 16, NT>(s, tw, tid);
-    __syncthreads();
-    fft_pass_inverse<M, 256, 16, NT>(s, tw, tid);
-    __syncthreads();
-    if constexpr (M == 8192) {
-        fft_pass_inverse<M, 4096, 16, NT>(s, tw, tid);
-        __syncthreads();
-        fft_pass_inverse<M, M, 2, NT>(s, tw, tid);
-        __syncthreads();
+    if constexpr (M <= 512) {
+        fft_small<M, NT, -1>(s, tw, tid);
     } else {
-        fft_pass_inverse<M, M, R1, NT>(s, tw, tid);
+        fft_pass_inverse<M, 16, 16, NT>(s, tw, tid);
         __syncthreads();
+        fft_pass_inverse<M, 256, 16, NT>(s, tw, tid);
+        __syncthreads();
+        if constexpr (M == 8192) {
+            fft_pass_inverse<M, 4096, 16, NT>(s, tw, tid);
+            __syncthreads();
+            fft_pass_inverse<M, M, 2, NT>(s, tw, tid);
+            __syncthreads();
+        } else {
+            constexpr int R1 = M / 256;
+            fft_pass_inverse<M, M, R1, NT>(s, tw, tid);
+            __syncthreads();
+        }
     }
 }
 
@@ -201,16 +246,26 @@ __device__ __forceinline__ void fft_inverse(double2* s, const double2* tw, int t
 template <int M>
 __host__ __device__ __forceinline__ constexpr int slot_of(int k)
 {
-    if (M == 8192) return (k % 2) * 4096 + ((k / 2) % 16) * 256 + ((k / 32) % 16) * 16 + (k / 512);
-    constexpr int R1 = M / 256;
-    return (k % R1) * 256 + ((k / R1) % 16) * 16 + (k / (R1 * 16));
+    if constexpr (M <= 512) {
+        return bitrev<M>(k); // short radix-2 transforms: plain bit reversal
+    } else if constexpr (M == 8192) {
+        return (k % 2) * 4096 + ((k / 2) % 16) * 256 + ((k / 32) % 16) * 16 + (k / 512);
+    } else {
+        constexpr int R1 = M / 256;
+        return (k % R1) * 256 + ((k / R1) % 16) * 16 + (k / (R1 * 16));
+    }
 }
 template <int M>
 __host__ __device__ __forceinline__ constexpr int freq_of(int slot)
 {
-    if (M == 8192) return (slot / 4096) + 2 * (((slot / 256) % 16) + 16 * (((slot / 16) % 16) + 16 * (slot % 16)));
-    constexpr int R1 = M / 256;
-    return (slot / 256) + R1 * (((slot / 16) % 16) + 16 * (slot % 16));
+    if constexpr (M <= 512) {
+        return bitrev<M>(slot);
+    } else if constexpr (M == 8192) {
+        return (slot / 4096) + 2 * (((slot / 256) % 16) + 16 * (((slot / 16) % 16) + 16 * (slot % 16)));
+    } else {
+        constexpr int R1 = M / 256;
+        return (slot / 256) + R1 * (((slot / 16) % 16) + 16 * (slot % 16));
+    }
 }
 
 } // namespace r8bgpu

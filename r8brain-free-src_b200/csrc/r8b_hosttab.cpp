@@ -71,6 +71,10 @@ void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec
         for (int k = keep; k <= M - keep; k++) nat[(size_t) k] = make_double2(0.0, 0.0);
     }
     switch (fft_log2) {
+    case 6: fill_slot_order<64>(nat, spec_slots); break;
+    case 7: fill_slot_order<128>(nat, spec_slots); break;
+    case 8: fill_slot_order<256>(nat, spec_slots); break;
+    case 9: fill_slot_order<512>(nat, spec_slots); break;
     case 10: fill_slot_order<1024>(nat, spec_slots); break;
     case 11: fill_slot_order<2048>(nat, spec_slots); break;
     case 13: fill_slot_order<8192>(nat, spec_slots); break;

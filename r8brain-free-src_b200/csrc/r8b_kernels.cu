@@ -181,6 +181,10 @@ void launch_blockconv(const BlockConvParams& p, const SrcView& src, const DstVie
     if (p.n_tiles <= 0 || n_ch <= 0) return;
     if (p.up == 1) {
         switch (p.fft_log2) {
+        case 6: launch_bc_inst<64, 1>(p, src, dst, n_ch, st); break;   // short kernels, reference-exact decimation
+        case 7: launch_bc_inst<128, 1>(p, src, dst, n_ch, st); break;
+        case 8: launch_bc_inst<256, 1>(p, src, dst, n_ch, st); break;
+        case 9: launch_bc_inst<512, 1>(p, src, dst, n_ch, st); break;
         case 10: launch_bc_inst<1024, 1>(p, src, dst, n_ch, st); break;
         case 11: launch_bc_inst<2048, 1>(p, src, dst, n_ch, st); break;
         case 13: launch_bc_inst<8192, 1>(p, src, dst, n_ch, st); break; // 1x stages only (one buffer)

@@ -8,6 +8,7 @@
 #include <unistd.h>
 
 #include <cctype>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -100,6 +101,10 @@ void* numa_host_alloc(size_t bytes, const std::vector<NumaRange>& ranges)
     const size_t total = (bytes + page - 1) / page * page;
     void* p = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (p == MAP_FAILED) return nullptr;
+#ifdef MADV_HUGEPAGE
+    // transparent huge pages, where the system grants them: 512x fewer IOMMU / page-table entries for the DMA engines
+    if (getenv("R8BGPU_NO_HUGEPAGES") == nullptr) madvise(p, total, MADV_HUGEPAGE);
+#endif
 #ifdef SYS_mbind
     for (const NumaRange& r : ranges) {
         if (r.node < 0 || r.node >= 64 || r.bytes == 0) continue;

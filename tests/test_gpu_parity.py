@@ -320,3 +320,74 @@ def test_tiny_blocks_and_many_channels(pkg, ref):
 def test_poly_bank_row_staging(pkg, ref, src, dst):
     ys, yr = run_both(pkg, ref, src, dst, [8192] * 5 + [333, 8192, 5], n_ch=2, max_in=8192)
     check(ys, yr)
+
+
+# ---- BASELINE block size (65536 frames per call) on every BASELINE chain: SURVEY.md appendix A count vectors -------------
+BASELINE_COUNTS = [
+    (48000.0, 44100.0, 0, [58679, 60211, 60211, 60211, 60212, 60211]),          # cfg 3
+    (48000.0, 47999.0, 0, [63835, 65535, 65534, 65535, 65535, 65534]),          # cfg 5
+    (192000.0, 44100.0, 0, [13516, 15053, 15052, 15053, 15053, 15053]),         # cfg 3b (first chain with CDSPHBDownsampler)
+    (44100.0, 2822400.0, 1, [3954306, 4194304, 4194304]),                       # cfg 4 (R8B_EXTFFT = 1)
+    (2822400.0, 44100.0, 1, [0, 0, 0, 347, 1024, 1024, 1024, 1024]),            # five half-band decimators (R8B_EXTFFT = 1)
+]
+
+
+@pytest.mark.parametrize("src,dst,extfft,counts", BASELINE_COUNTS)
+def test_baseline_block_size_counts_and_parity(pkg, ref, ref_e1, src, dst, extfft, counts):
+    oracle = ref_e1 if extfft else ref
+    n_ch, l = 2, 65536
+    x = ou.white_noise(n_ch, l * len(counts), 11)
+    rb = pkg.ResamplerBatch(n_ch, src, dst, l, 2.0, pkg.ATTEN_24, device=0, extfft=extfft)
+    rs = [oracle.Resampler(src, dst, l, 2.0, pkg.ATTEN_24) for _ in range(n_ch)]
+    for i, want in enumerate(counts):
+        y = rb.process(x[:, i * l:(i + 1) * l])
+        assert y.shape[1] == want, (i, y.shape[1], want)
+        for c in range(n_ch):
+            yr = rs[c].process(x[c, i * l:(i + 1) * l])
+            assert len(yr) == want
+            if want:
+                m, r = ou.parity_metrics(y[c], yr)
+                assert m <= MAX_TOL and r <= RMS_TOL, (i, c, m / ou.EPS, r / ou.EPS)
+
+
+def test_bench_shape_device_pointers_on_a_user_stream(pkg, ref):
+    """The exact shape bench.py times: 1024 channels x 65536 frames through r8bgpu_batch_process() on a non-default
+    stream, padded output rows; sampled channels against the oracle, every channel for finiteness and count."""
+    import torch
+    n_ch, l, calls = 1024, 65536, 3
+    plan = pkg.Plan(44100.0, 96000.0, l, 2.0, pkg.ATTEN_24)
+    batch = pkg.Batch(plan, n_ch, 0)
+    dev = torch.device("cuda", 0)
+    cap = (plan.max_out_len + 7) // 8 * 8
+    rng = np.random.default_rng(2024)
+    xs = [rng.uniform(-1.0, 1.0, size=(n_ch, l)) for _ in range(2)]
+    dx = [torch.from_numpy(a).to(dev) for a in xs]
+    out = torch.empty((n_ch, cap), dtype=torch.float64, device=dev)
+    st = torch.cuda.Stream(dev)
+    batch.set_stream(st.cuda_stream)
+    check_ch = [0, 1, 341, 682, 1023]
+    rs = {c: ref.Resampler(44100.0, 96000.0, l, 2.0, pkg.ATTEN_24) for c in check_ch}
+    want = [138963, 142664, 142663]
+    for i in range(calls):
+        with torch.cuda.stream(st):
+            n = batch.process_ptr(dx[i & 1].data_ptr(), l, l, out.data_ptr(), cap, cap)
+        st.synchronize()
+        assert n == want[i]
+        y = out[:, :n].cpu().numpy()
+        assert np.all(np.isfinite(y))
+        for c in check_ch:
+            yr = rs[c].process(xs[i & 1][c])
+            assert len(yr) == n
+            m, r = ou.parity_metrics(y[c], yr)
+            assert m <= MAX_TOL and r <= RMS_TOL, (i, c, m / ou.EPS, r / ou.EPS)
+    batch.set_stream(None)
+
+
+@pytest.mark.parametrize("src,dst", [(96000.0, 48000.0), (192000.0, 48000.0), (352800.0, 44100.0), (48000.0, 36000.0)])
+@pytest.mark.parametrize("tb", [10.0, 20.0, 45.0])
+def test_short_kernels_reference_exact_decimation(pkg, ref, src, dst, tb):
+    """Wide transition bands make the low-pass kernel short; the reference then runs its power-of-two decimation on
+    blocks of 64..512 points, and reference-exact results need tiles of exactly that size (radix-2 transforms)."""
+    for atten in (pkg.ATTEN_16IR, pkg.ATTEN_24):
+        ys, yr = run_both(pkg, ref, src, dst, [3000, 1, 4096, 777, 4096], n_ch=2, tb=tb, atten=atten, max_in=4096)
+        check(ys, yr)

@@ -37,8 +37,10 @@ def test_random_rates_and_chunkings(pkg, ref, seed):
         try:
             rb = pkg.ResamplerBatch(2, src, dst, max_in, tb, atten, device=0)
         except pkg.R8bGpuError as e:
-            # only documented gaps may be refused (kernels longer than the largest tile)
-            assert "too long" in str(e), (src, dst, tb, atten, str(e))
+            # only the documented gap may be refused: a low-pass kernel longer than the largest tile, which for these
+            # transition bands (>= 1.5 %) cannot happen below ~3300 taps -- checked against the plan itself
+            klen = max(s["kernel_len"] for s in pkg.Plan(src, dst, max_in, tb, atten).stages() if s["name"] == "blockconv")
+            assert "too long" in str(e) and klen > 3300, (src, dst, tb, atten, klen, str(e))
             continue
         rs = [ref.Resampler(src, dst, max_in, tb, atten) for _ in range(2)]
         pos = 0
