@@ -123,6 +123,7 @@ struct StageDev {
     double2* c_tab = nullptr;   // v2 fused kernel: phase C operands in thread order
     bool bank_frag_order = false; // grouped bank stored in mma fragment order (only the tensor-path interpolation reads it)
     bool f2_ok = false;
+    bool f2_copy = false; // BlockConvolver 2/1 alone on the v2 kernel (phase E copies the 2x stream out)
     FusedGeom fgeom;
 };
 
@@ -534,6 +535,18 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                     return nullptr;
                 }
             }
+            // a 2x BlockConvolver that no interpolator follows runs on the v2 fused kernel too (its phase E copies the stream
+            // out) when the polyphase branches fit 4096-point tiles
+            if (!d.fused_with_next && s.up == 2 && s.down == 1 && !s.block_exact && !getenv("R8BGPU_NO_FUSION") &&
+                !getenv("R8BGPU_FUSED_V1") && 2 * (4096 - 2 * d.lg) >= 2048) {
+                d.f2_copy = true;
+                d.fgeom = FusedGeom();
+                d.fgeom.ok = true;
+                d.fgeom.up = 2;
+                d.fgeom.lg = d.lg;
+                d.fgeom.span_max = (2 * (4096 - 2 * d.lg)) & ~3;
+                d.fft_log2 = 12;
+            }
             if (d.fused_with_next) d.fft_log2 = 12; // the fused kernel is built for M = 4096
             if (d.fft_log2 < 0) {
                 set_err("batch_create: low-pass kernel too long for the in-shared-memory FFT tiles");
@@ -547,7 +560,7 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
             if (!cuda_ok(cudaMemcpy(d.spec, spec.data(), nb, cudaMemcpyHostToDevice), "copy spec")) return nullptr;
             if (!cuda_ok(cudaMemcpy(d.tw, tw.data(), nb, cudaMemcpyHostToDevice), "copy tw")) return nullptr;
             b->dev_bytes += 2 * nb;
-            if (d.fused_with_next) { // conflict-free [q][r] twiddle tables, one 8 KB bulk copy per CTA in the v2 kernel
+            if (d.fused_with_next || d.f2_copy) { // conflict-free [q][r] twiddle tables, one 8 KB bulk copy per CTA in the v2 kernel
                 const std::vector<double2> tt = build_tw_tab(tw);
                 if (!cuda_ok(cudaMalloc(&d.tw_tab, tt.size() * sizeof(double2)), "cudaMalloc(tw_tab)")) return nullptr;
                 if (!cuda_ok(cudaMemcpy(d.tw_tab, tt.data(), tt.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy tw_tab")) return nullptr;
@@ -758,7 +771,7 @@ int r8bgpu_batch_stage_kernel(const r8bgpu_batch* b, int stage, char* name, int 
         span = d.casc_len;
     } else {
         switch (s.kind) {
-        case ST_BLOCKCONV: nm = "k_blockconv"; break;
+        case ST_BLOCKCONV: nm = d.f2_copy ? "k_up2_frac2<copy>" : "k_blockconv"; break;
         case ST_FRAC_WHOLE: nm = "k_frac<false>"; break;
         case ST_FRAC_POLY: nm = "k_frac<true>"; break;
         case ST_HBUP: nm = "k_hbup"; break;
@@ -1048,6 +1061,32 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
         } else
         switch (s.kind) {
         case ST_BLOCKCONV: {
+            if (d.f2_copy) {
+                FusedParams fp;
+                memset(&fp, 0, sizeof fp);
+                fp.mode = 2;
+                fp.e0 = c.e0;
+                fp.e1 = c.e1;
+                fp.p_lo = c.e0 & ~1LL;
+                fp.p_hi = c.e1;
+                fused2_tiles(fp, d.fgeom, i == 0 ? (int) (c.n0 & 1) : -1);
+                fp.lg = d.lg;
+                fp.ysh = 31;
+                fp.spec = d.spec;
+                fp.tw = d.tw;
+                fp.tw_tab = d.tw_tab;
+                fp.c_tab = d.c_tab;
+                fp.up = 2;
+                fp.ylen = 8192;
+                fp.ir = 8;
+                fp.out_step = 8; // one (unused) phase group
+                fp.smaxp = 4;
+                fp.n_ch = nch;
+                fp.flags = b->f2_flags & 2;
+                launch_up2_frac2(fp, src, dst, b->n_sm, st);
+                b->launches++;
+                break;
+            }
             BlockConvParams p;
             const int up_eff = d.virt_up > 1 ? 1 : s.up;
             p.up = up_eff;

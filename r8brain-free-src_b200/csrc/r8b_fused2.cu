@@ -134,7 +134,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // TC: interpolation as 8x8x4 fp64 matrix products (IRV == 8; GLOG unused)
 // UP: up-factor of the BlockConvolver (2: 4096-point complex inverse, 8192 stream samples per tile; 1: 2048-point inverse
 // mirroring the real-input forward transform, 4096 samples per tile -- TC only)
-template <int IRV, bool PADV, int GLOG, bool TC, int UP = 2>
+// COPY: no interpolator follows -- phase E writes the tile's owned positions of the 2x-rate stream to the destination
+// (the BlockConvolver 2/1 alone: chains that continue with half-band upsamplers, or end there); no bank is loaded.
+template <int IRV, bool PADV, int GLOG, bool TC, int UP = 2, bool COPY = false>
 __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ FusedParams p, const __grid_constant__ SrcView src,
                                                       const __grid_constant__ DstView dst)
 {
@@ -158,13 +160,14 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
         for (int i = 0; i < 5; i++) mbar_init(&mb[i], 1);
         fence_mbar_init();
     }
-    if (tid < n_groups) s_goff[tid] = __ldg(&p.goff[p.delta + tid * IRV]);
+    if (!COPY && tid < n_groups) s_goff[tid] = __ldg(&p.goff[p.delta + tid * IRV]);
     __syncthreads();
     if (tid == 0) {
         // tables: one transaction barrier, 1 + n_groups bulk copies
-        mbar_expect_tx(&mb[0], (uint32_t) (512 * sizeof(double2) + (size_t) n_groups * esz * sizeof(double)));
+        const int n_bank = COPY ? 0 : n_groups;
+        mbar_expect_tx(&mb[0], (uint32_t) (512 * sizeof(double2) + (size_t) n_bank * esz * sizeof(double)));
         bulk_g2s(tw2, p.tw_tab, 512 * sizeof(double2), &mb[0]);
-        for (int g = 0; g < n_groups; g++)
+        for (int g = 0; g < n_bank; g++)
             bulk_g2s(sbank + g * esz, p.gbank + (long long) (p.delta + g * IRV) * esz, (uint32_t) (esz * sizeof(double)), &mb[0]);
         mbar_arrive(&mb[3]); // half 0 interpolates first
     }
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
             }
             fwd_pass1_r8(v, buf, tw2, twf, ht);
         }
-        if (ht == HT - 1) interp_prepare(p, dst, t, s_i[h], &s_o[h]);
+        if (!COPY && ht == HT - 1) interp_prepare(p, dst, t, s_i[h], &s_o[h]);
         bar_half(h);
         // B. the two radix-16 passes act on 256-point blocks owned by one half-warp each
         if (ht < FN / 16) {
@@ -272,7 +275,21 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
         {
             const double* yb = reinterpret_cast<const double*>(buf);
             const int* si = s_i[h];
-            if constexpr (TC) {
+            if constexpr (COPY) {
+                // owned positions [A0, A1) clipped to this call's range; position q sits at y index q - 2 w
+                long long q0 = t.A0 > p.e0 ? t.A0 : p.e0, q1 = t.A1 < p.e1 ? t.A1 : p.e1;
+                const int off = (int) (q0 - 2 * t.w), cnt = q1 > q0 ? (int) (q1 - q0) : 0;
+                double* const orow = dst.ptr + (long long) t.ch * dst.stride;
+                const long long d0 = q0 - dst.base;
+                const bool pair_ok = ((off | (int) (d0 & 1)) & 1) == 0 && (reinterpret_cast<unsigned long long>(orow) & 15) == 0;
+                if (pair_ok) { // even start on both sides: 16-byte moves (a pair never straddles the ring's end)
+                    for (int i = 2 * ht; i + 1 < cnt; i += 2 * HT)
+                        *reinterpret_cast<double2*>(orow + ((d0 + i) & dst.mask)) = *reinterpret_cast<const double2*>(yb + off + i);
+                    if ((cnt & 1) && ht == 0) orow[(d0 + cnt - 1) & dst.mask] = yb[off + cnt - 1];
+                } else {
+                    for (int i = ht; i < cnt; i += HT) orow[(d0 + i) & dst.mask] = yb[off + i];
+                }
+            } else if constexpr (TC) {
                 MmaTile mt;
                 mt.load(si);
                 const int n_mu = mt.n_j > 0 ? mma_units(p, mt.c_cnt) : 0, ksteps = p.smaxp >> 2;
@@ -339,11 +356,11 @@ int fused2_smem_bytes(int bank_doubles, bool staged)
 }
 int fused2_stage_off(int bank_doubles) { return 2 * (2 * FPL + 512) + ((bank_doubles + 1) & ~1); }
 
-template <int IRV, bool PADV, int GLOG, bool TC = false, int UP = 2>
+template <int IRV, bool PADV, int GLOG, bool TC = false, int UP = 2, bool COPY = false>
 static void launch_inst2(const FusedParams& p, const SrcView& src, const DstView& dst, int grid, int smem, cudaStream_t st)
 {
-    ensure_dyn_smem<k_up2_frac2<IRV, PADV, GLOG, TC, UP>>(227 * 1024);
-    k_up2_frac2<IRV, PADV, GLOG, TC, UP><<<(unsigned) grid, NT2, smem, st>>>(p, src, dst);
+    ensure_dyn_smem<k_up2_frac2<IRV, PADV, GLOG, TC, UP, COPY>>(227 * 1024);
+    k_up2_frac2<IRV, PADV, GLOG, TC, UP, COPY><<<(unsigned) grid, NT2, smem, st>>>(p, src, dst);
 }
 
 // p.n_ch, p.n_tiles, p.span ... describe the call; n_sm = SMs of the device (persistent grid).
@@ -358,6 +375,10 @@ void launch_up2_frac2(const FusedParams& p, const SrcView& src, const DstView& d
 #define R8B_F2_CASE(IRV, GL)                                                              \
     if (pad) launch_inst2<IRV, true, GL>(p, src, dst, grid, smem, st);                    \
     else launch_inst2<IRV, false, GL>(p, src, dst, grid, smem, st);
+    if (p.mode == 2) { // BlockConvolver 2/1 alone
+        launch_inst2<8, false, 0, true, 2, true>(p, src, dst, grid, smem, st);
+        return;
+    }
     if (p.up == 1) { // batch_create only routes a 1x pair here when the tensor-path bank fits
         if (pad) launch_inst2<8, true, 0, true, 1>(p, src, dst, grid, smem, st);
         else launch_inst2<8, false, 0, true, 1>(p, src, dst, grid, smem, st);

@@ -122,7 +122,7 @@ void launch_hbup_cascade(const HbCascadeParams& p, int smem_bytes, const SrcView
 // Fused 2x BlockConvolver + fractional interpolator (r8b_fused.cu).  Positions are indices of the
 // 2x-rate stream between the two stages.
 struct FusedParams {
-    int mode;              // 0 whole stepping, 1 order-2 bank
+    int mode;              // 0 whole stepping, 1 order-2 bank, 2 (v2 kernel only) no interpolator: the 2x stream itself is the output
     int n_tiles;           // tiles of `span` owned positions each, processed in pairs
     int stage_off;         // offset (doubles) of the store staging area in dynamic smem, 0 = none
     int debug;             // profiling experiments only (R8BGPU_DEBUG): bit0 skip interp stores, bit1 skip tap loop
