@@ -929,7 +929,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             const int nbuf = p.fuse_last2 ? cl - 1 : cl; // streams 0 .. nbuf-1 live in shared memory
             int halo = 0;
             for (int k = 0; k < nbuf; k++) halo += p.lo_off[k] + p.hi_off[k] + 8;
-            int budget = 14336; // doubles of shared memory per CTA (2 CTAs per SM; measured best); buffers carry a 5/4 skew
+            int budget = 7000; // doubles of shared memory per CTA (4 CTAs of 128 threads per SM; measured best); buffers carry a 5/4 skew
             if (const char* e = getenv("R8BGPU_HB_SMEM_DOUBLES")) budget = atoi(e);
             int w = (((budget * 4) / 5 - halo) / ((1 << nbuf) - 1)) & ~31;
             if (w > 1024) w = 1024;

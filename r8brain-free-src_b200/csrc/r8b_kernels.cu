@@ -512,7 +512,7 @@ void launch_save_tail(const double* cur, long long cur_stride, long long cur_bas
 // corresponding w * 2^c samples of s_c.
 //   s_{k+1}[2n] = s_k[n];  s_{k+1}[2n+1] = sum_j f_k[j] * (s_k[n-j] + s_k[n+1+j]);  s_k[<0] = 0.
 #ifndef R8BGPU_HB_NT
-#define R8BGPU_HB_NT 256
+#define R8BGPU_HB_NT 128 // CTA shape: see the note at k_hbup_cascade
 #endif
 constexpr int HB_NT = R8BGPU_HB_NT;
 __device__ __forceinline__ int hb_pad(int i) { return i + (i >> 2); }
@@ -656,11 +656,11 @@ __device__ __forceinline__ void hb_last2_dispatch(int t2, const double* in, long
     }
 }
 
-#ifndef R8BGPU_HB_NT
-#define R8BGPU_HB_NT 256
-#endif
+// CTA shape of the cascade.  The kernel is bound by the block-wide barriers between its stage passes, not by a pipe, so
+// more, smaller CTAs per SM overlap better: 4 x 128 threads with ~55 KB tiles measured 1.33 ms on cfg 4 against 1.45 ms
+// for 2 x 256 threads with ~110 KB tiles (124 registers either way, no spills; 384 / 512 threads were slower still).
 #ifndef R8BGPU_HB_MINB
-#define R8BGPU_HB_MINB 2 // two CTAs per SM is what the shared-memory tile allows; 123 registers, no spills (3: 80 + spills, slower)
+#define R8BGPU_HB_MINB 4
 #endif
 __global__ void __launch_bounds__(HB_NT, R8BGPU_HB_MINB) k_hbup_cascade(HbCascadeParams p, SrcView src, DstView dst)
 {

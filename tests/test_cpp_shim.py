@@ -69,3 +69,58 @@ def test_shim_process_matches_reference(pkg, ref, tmp_path):
         assert len(yr) == n
         m, rr = ou.parity_metrics(y, yr)
         assert m <= 32 * ou.EPS and rr <= 4 * ou.EPS
+
+
+# ---- the reference's DLL interface (DLL/r8bsrc.h): libr8bsrc.so driven from plain C -------------------------------------
+DLL_EXE = os.path.join(ROOT, "tests", "cpp", "dll_demo")
+
+
+def build_dll_demo(pkg):
+    lib_dir = os.path.dirname(pkg.lib_path())
+    dll = os.path.join(lib_dir, "libr8bsrc.so")
+    if not os.path.exists(dll):
+        pytest.skip("libr8bsrc.so not built (no g++ at build time)")
+    src = os.path.join(ROOT, "tests", "cpp", "dll_demo.c")
+    if os.path.exists(DLL_EXE) and os.path.getmtime(DLL_EXE) > max(os.path.getmtime(src), os.path.getmtime(dll)):
+        return DLL_EXE
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        if os.path.exists(DLL_EXE):
+            return DLL_EXE
+        pytest.skip("no gcc and no prebuilt demo")
+    subprocess.run([gcc, "-O1", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", DLL_EXE,
+                    "-L", lib_dir, "-lr8bsrc", "-lr8bgpu", "-Wl,-rpath," + lib_dir], check=True)
+    return DLL_EXE
+
+
+def test_dll_interface_exports_and_inlen(pkg, ref):
+    exe = build_dll_demo(pkg)
+    import ctypes
+    L = ctypes.CDLL(os.path.join(os.path.dirname(pkg.lib_path()), "libr8bsrc.so"))
+    for name in ("r8b_create", "r8b_delete", "r8b_inlen", "r8b_clear", "r8b_process"):  # DLL/r8bsrc.h:71-134
+        assert hasattr(L, name)
+    for res, atten in ((0, 136.45), (1, 109.56), (2, 180.15)):
+        out = subprocess.run([exe, "--inlen", "44100", "96000", "4096", str(res), "1000"], capture_output=True, text=True, check=True)
+        assert int(out.stdout) == ref.Resampler(44100.0, 96000.0, 4096, 2.0, atten).input_required_for_output(1000)
+
+
+@pytest.mark.gpu
+def test_dll_interface_process_matches_reference(pkg, ref, tmp_path):
+    exe = build_dll_demo(pkg)
+    frames, block = 30000, 4096
+    x = ou.white_noise(1, frames, 9)[0]
+    fin, fout = str(tmp_path / "in.f64"), str(tmp_path / "out.f64")
+    x.tofile(fin)
+    for res, atten in ((0, 136.45), (2, 180.15)):
+        out = subprocess.run([exe, fin, fout, str(frames), "48000", "44100", str(block), str(res)], capture_output=True, text=True, check=True)
+        y = np.fromfile(fout, dtype=np.float64)
+        # the demo clears after the first block and feeds it again: the stream restarts
+        r = ref.Resampler(48000.0, 44100.0, block, 2.0, atten)
+        parts = [r.process(x[:block])]          # written before the clear
+        r.clear()
+        r.process(x[:block])                    # re-fed after the clear (not written)
+        parts += [r.process(x[i:i + block]) for i in range(block, frames, block)]
+        yr = np.concatenate(parts)
+        assert int(out.stdout) == len(yr) == len(y)
+        m, rr = ou.parity_metrics(y, yr)
+        assert m <= 32 * ou.EPS and rr <= 4 * ou.EPS
