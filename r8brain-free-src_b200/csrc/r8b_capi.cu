@@ -853,8 +853,28 @@ static bool upload_fasttiming(r8bgpu_batch* b, cudaStream_t st)
 
 // Launches every kernel of one process() call (already scheduled in b->calls) for the channel range
 // [ch0, ch0+nch) on stream st.  d_in / d_out point at the FIRST channel of that range.
+// TypedIO: when the first / last kernel of the chain converts caller-side sample formats itself (fuses_input_format(),
+// fuses_output_format()), d_in / d_out address planar samples of that format and the strides count samples.
+struct TypedIO {
+    int in_fmt = FMT_F64, out_fmt = FMT_F64;
+    double in_scale = 1.0, out_scale = 1.0;
+};
+
+// The v2 fused kernel widens a planar typed block while it gathers its tiles / narrows in its tensor-path stores.
+static bool fuses_input_format(const r8bgpu_batch* b)
+{
+    return !b->plan->passthrough && !b->dev.empty() && ((b->dev[0].fused_with_next && b->dev[0].f2_ok &&
+           b->plan->stages[1].kind == ST_FRAC_WHOLE) || b->dev[0].f2_copy) && !getenv("R8BGPU_NO_FORMAT_FUSION");
+}
+static bool fuses_output_format(const r8bgpu_batch* b)
+{
+    const size_t ns = b->dev.size();
+    return !b->plan->passthrough && ns >= 2 && b->plan->stages[ns - 1].kind == ST_FRAC_WHOLE && b->dev[ns - 1].fused_into_prev &&
+           b->dev[ns - 2].f2_ok && b->dev[ns - 1].bank_frag_order && !getenv("R8BGPU_NO_FORMAT_FUSION");
+}
+
 static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, int l, double* d_out,
-                        size_t out_stride, int ch0, int nch, cudaStream_t st)
+                        size_t out_stride, int ch0, int nch, cudaStream_t st, const TypedIO& tio = TypedIO())
 {
     const Plan& P = *b->plan;
     const size_t ns = P.stages.size();
@@ -874,6 +894,8 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             src.cur = d_in;
             src.cur_stride = (long long) in_stride;
             src.cur_base = c.n0;
+            src.cur_fmt = tio.in_fmt;
+            src.cur_scale = tio.in_scale;
         } else {
             src.cur = nullptr;
             src.cur_stride = 0;
@@ -886,6 +908,8 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             dst.stride = (long long) out_stride;
             dst.mask = -1;
             dst.base = b->calls[last].e0;
+            dst.fmt = tio.out_fmt;
+            dst.scale = tio.out_scale;
         } else {
             dst.ptr = b->dev[last + 1].ring + (long long) ch0 * b->dev[last + 1].ring_cap;
             dst.stride = b->dev[last + 1].ring_cap;
@@ -1173,7 +1197,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
         long long from = c0.n1 - d0.ring_cap;
         if (from < c0.n0) from = c0.n0;
         launch_save_tail(d_in, (long long) in_stride, c0.n0, from, c0.n1, d0.ring + (long long) ch0 * d0.ring_cap, d0.ring_cap,
-                         d0.ring_cap - 1, nch, st);
+                         d0.ring_cap - 1, nch, st, tio.in_fmt, tio.in_scale);
         b->launches++;
     }
 }
@@ -1368,18 +1392,29 @@ static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, co
         }
         cudaEventRecord(b->ev_h2d[(size_t) gi], b->s_h2d);
         cudaStreamWaitEvent(b->s_comp, b->ev_h2d[(size_t) gi], 0);
-        if (!in_plain) {
+        TypedIO tio;
+        const bool in_fused = !in_plain && !in.interleaved && fuses_input_format(b);
+        const bool out_fused = !out_plain && !out.interleaved && fuses_output_format(b);
+        if (in_fused) {
+            tio.in_fmt = in.format;
+            tio.in_scale = in.scale;
+        } else if (!in_plain) {
             launch_to_f64(in.format, rin, in.interleaved != 0, in.interleaved ? (size_t) nch : in_cap, din, in_cap, l,
                           nch, in.scale, b->s_comp);
             if (l > 0) b->launches++;
+        }
+        if (out_fused) {
+            tio.out_fmt = out.format;
+            tio.out_scale = out.scale;
         }
         if (P.passthrough) {
             if (l > 0) cudaMemcpy2DAsync(dout, o_cap * sizeof(double), din, in_cap * sizeof(double),
                                          (size_t) l * sizeof(double), (size_t) nch, cudaMemcpyDeviceToDevice, b->s_comp);
         } else {
-            launch_call(b, din, in_cap, l, dout, o_cap, ch0, nch, b->s_comp);
+            launch_call(b, in_fused ? (const double*) rin : din, in_cap, l, out_fused ? (double*) rout : dout, o_cap, ch0, nch,
+                        b->s_comp, tio);
         }
-        if (!out_plain) {
+        if (!out_plain && !out_fused) {
             launch_from_f64(out.format, rout, out.interleaved != 0, out.interleaved ? (size_t) nch : o_cap, dout, o_cap,
                             n, nch, out.scale, b->s_comp);
             if (n > 0) b->launches++;
@@ -1480,22 +1515,32 @@ int r8bgpu_batch_process_fmt(r8bgpu_batch* b, const r8bgpu_buffer* d_in, int l, 
     }
     const double* src = (const double*) d_in->data;
     size_t src_stride = d_in->stride;
-    if (!in_plain) {
+    TypedIO tio;
+    const bool in_fused = !in_plain && !d_in->interleaved && fuses_input_format(b);
+    const bool out_fused = !out_plain && !d_out->interleaved && fuses_output_format(b);
+    if (in_fused) { // the first kernel reads the caller's samples as they are
+        tio.in_fmt = d_in->format;
+        tio.in_scale = d_in->scale;
+    } else if (!in_plain) {
         launch_to_f64(d_in->format, d_in->data, d_in->interleaved != 0, d_in->stride, b->st_in, in_cap, l, b->n_ch,
                       d_in->scale, st);
         if (l > 0) b->launches++;
         src = b->st_in;
         src_stride = in_cap;
     }
-    double* dst = out_plain ? (double*) d_out->data : b->st_out;
-    const size_t dst_stride = out_plain ? d_out->stride : o_cap;
+    double* dst = (out_plain || out_fused) ? (double*) d_out->data : b->st_out;
+    const size_t dst_stride = (out_plain || out_fused) ? d_out->stride : o_cap;
+    if (out_fused) { // the last kernel narrows in its stores
+        tio.out_fmt = d_out->format;
+        tio.out_scale = d_out->scale;
+    }
     if (P.passthrough) {
         if (l > 0) cudaMemcpy2DAsync(dst, dst_stride * sizeof(double), src, src_stride * sizeof(double),
                                      (size_t) l * sizeof(double), (size_t) b->n_ch, cudaMemcpyDeviceToDevice, st);
     } else {
-        launch_call(b, src, src_stride, l, dst, dst_stride, 0, b->n_ch, st);
+        launch_call(b, src, src_stride, l, dst, dst_stride, 0, b->n_ch, st, tio);
     }
-    if (!out_plain) {
+    if (!out_plain && !out_fused) {
         launch_from_f64(d_out->format, d_out->data, d_out->interleaved != 0, d_out->stride, b->st_out, o_cap, n, b->n_ch,
                         d_out->scale, st);
         if (n > 0) b->launches++;

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
             tn = tile_of(p, u + stride);
             pathn = tile_input_path(src, tn);
             if (pathn == 2 && !tma_in) pathn = 1;
-            if (pathn != 0 && ht == 0) bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<unsigned long long>(tile_src(tn)) & ~15ull),
+            if ((pathn == 1 || pathn == 2) && ht == 0) bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<unsigned long long>(tile_src(tn)) & ~15ull),
                                                         FM * sizeof(double));
         }
         // A. input -> registers -> radix-8 pass into the lower half of the buffer

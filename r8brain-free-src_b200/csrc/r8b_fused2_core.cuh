@@ -49,7 +49,8 @@ R8B_HD Tile tile_of(const FusedParams& p, int u)
 // source ring when the window neither wraps nor reaches past the samples written so far (later stages).
 R8B_HD const double* tile_run(const SrcView& src, const Tile& t)
 {
-    if (t.w >= src.cur_base && t.w + FM <= src.avail) return src.cur + (long long) t.ch * src.cur_stride + (t.w - src.cur_base);
+    if (t.w >= src.cur_base && t.w + FM <= src.avail)
+        return src.cur_fmt == FMT_F64 ? src.cur + (long long) t.ch * src.cur_stride + (t.w - src.cur_base) : nullptr;
     if (t.w >= 0 && t.w + FM <= src.avail && t.w + FM <= src.cur_base) {
         const long long i0 = t.w & src.ring_mask;
         if (i0 + FM <= src.ring_mask + 1) return src.ring + (long long) t.ch * src.ring_stride + i0;
@@ -58,9 +59,11 @@ R8B_HD const double* tile_run(const SrcView& src, const Tile& t)
 }
 
 // Which way the samples arrive: 0 = every sample individually (history ring across a wrap, before the start, or past
-// the available input), 1 = plain loads from a contiguous run, 2 = one bulk copy (16-byte aligned run).
+// the available input), 1 = plain loads from a contiguous run, 2 = one bulk copy (16-byte aligned run), 3 = a run of
+// the caller's block in a narrower sample format, widened while it is gathered.
 R8B_HD int tile_input_path(const SrcView& src, const Tile& t)
 {
+    if (src.cur_fmt != FMT_F64 && t.w >= src.cur_base && t.w + FM <= src.avail) return 3;
     const double* a = tile_run(src, t);
     if (a == nullptr) return 0;
     return (reinterpret_cast<unsigned long long>(a) & 15) == 0 ? 2 : 1;
@@ -69,7 +72,13 @@ R8B_HD int tile_input_path(const SrcView& src, const Tile& t)
 // z[m], m = r + 256 j, straight from global memory (paths 0 and 1)
 R8B_HD void gather_tile(double2 (&v)[8], const SrcView& src, const Tile& t, int path, int r)
 {
-    if (path != 0) {
+    if (path == 3) {
+        const long long i0 = (long long) t.ch * src.cur_stride + (t.w - src.cur_base) + 2 * r;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            v[j] = make_double2(typed_load(src.cur, i0 + 512 * j, src.cur_fmt, src.cur_scale),
+                                typed_load(src.cur, i0 + 512 * j + 1, src.cur_fmt, src.cur_scale));
+    } else if (path != 0) {
         const double* __restrict__ a = tile_run(src, t) + 2 * r;
         if ((reinterpret_cast<unsigned long long>(a) & 15) == 0) {
 #pragma unroll
@@ -279,6 +288,9 @@ R8B_HD void interp_prepare(const FusedParams& p, const DstView& dst, const Tile&
     s_i[2] = (int) (c_first * p.out_step - ja);
     s_i[3] = (int) (c_first * p.in_step - p.fll - (p.up == 1 ? 1 : 2) * t.w);
     *s_op = dst.ptr + (long long) t.ch * dst.stride + ((ja - dst.base) & dst.mask);
+    const long long e0 = (long long) t.ch * dst.stride + (ja - dst.base); // typed destinations: element index, [4..5]
+    s_i[4] = (int) (e0 & 0xffffffffLL);
+    s_i[5] = (int) (e0 >> 32);
 }
 
 // Lane geometry of the interpolation: a warp covers CL = 32 >> GLOG stepping cycles x GL = 1 << GLOG phase
@@ -431,12 +443,14 @@ struct MmaUnit {
 // Tile-level values every unit needs (read once per tile from the bookkeeping interp_prepare() left in shared memory)
 struct MmaTile {
     int n_j, c_cnt, jshift, wbase;
+    long long elem0; // element index of the tile's first output in a typed linear destination
     R8B_HD void load(const int* __restrict__ s_i)
     {
         n_j = s_i[0];
         c_cnt = s_i[1];
         jshift = s_i[2];
         wbase = s_i[3];
+        elem0 = (long long) (unsigned int) s_i[4] | ((long long) s_i[5] << 32);
     }
 };
 
@@ -465,7 +479,10 @@ R8B_HD void mma_store(const FusedParams& p, const DstView& dst, int ch, const Mm
     const int j = c * p.out_step + rr + mt.jshift;
     const bool in0 = (p.wrap || rr < p.out_step) && j >= 0 && j < mt.n_j;
     const bool in1 = (p.wrap || rr + 1 < p.out_step) && j + 1 >= 0 && j + 1 < mt.n_j;
-    if (dst.mask == -1) {
+    if (dst.fmt != FMT_F64) { // narrow on the way out (linear destinations only): the casts of oneshot<Tin,Tout>()
+        if (in0) typed_store(dst.ptr, mt.elem0 + j, dst.fmt, dst.scale, c0);
+        if (in1) typed_store(dst.ptr, mt.elem0 + j + 1, dst.fmt, dst.scale, c1);
+    } else if (dst.mask == -1) {
         double* o = s_o + j;
         if (in0 && in1 && (reinterpret_cast<unsigned long long>(o) & 15) == 0) {
             *reinterpret_cast<double2*>(o) = make_double2(c0, c1);

@@ -8,10 +8,65 @@
 
 namespace r8bgpu {
 
+// One sample of a planar typed block, widened exactly ((double) of the stored value) and scaled with a correctly
+// rounded multiply -- bit for bit what k_cvt_planar (r8b_format.cu) produces.
+R8B_HD double typed_load(const void* base, long long idx, int fmt, double scale)
+{
+    double x;
+    switch (fmt) {
+    case FMT_F32: x = (double) R8B_LDG(reinterpret_cast<const float*>(base) + idx); break;
+    case FMT_S16: x = (double) R8B_LDG(reinterpret_cast<const short*>(base) + idx); break;
+    case FMT_S32: x = (double) R8B_LDG(reinterpret_cast<const int*>(base) + idx); break;
+    case FMT_S24: {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(base) + 3 * idx; // packed little-endian
+        x = (double) ((int) R8B_LDG(p) | ((int) R8B_LDG(p + 1) << 8) | ((int) (signed char) R8B_LDG(p + 2) << 16));
+        break;
+    }
+    default: x = R8B_LDG(reinterpret_cast<const double*>(base) + idx); break;
+    }
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(x, scale);
+#else
+    return x * scale;
+#endif
+}
+
+// (T) (y * scale): float rounds to nearest, integers truncate toward zero and saturate, NaN -> 0 (r8b_format.cu)
+R8B_HD void typed_store(void* base, long long idx, int fmt, double scale, double y)
+{
+#ifdef __CUDA_ARCH__
+    y = __dmul_rn(y, scale);
+#else
+    y = y * scale;
+#endif
+    if (fmt == FMT_F32) {
+        reinterpret_cast<float*>(base)[idx] = (float) y;
+        return;
+    }
+    long long lo = -2147483647LL - 1, hi = 2147483647LL;
+    if (fmt == FMT_S16) lo = -32768, hi = 32767;
+    if (fmt == FMT_S24) lo = -8388608, hi = 8388607;
+    long long v = 0;
+    if (y == y) v = y <= (double) lo ? lo : (y >= (double) hi ? hi : (long long) y); // C cast truncates toward zero
+    if (fmt == FMT_S16) {
+        reinterpret_cast<short*>(base)[idx] = (short) v;
+    } else if (fmt == FMT_S32) {
+        reinterpret_cast<int*>(base)[idx] = (int) v;
+    } else {
+        unsigned char* p = reinterpret_cast<unsigned char*>(base) + 3 * idx;
+        p[0] = (unsigned char) (v & 0xff);
+        p[1] = (unsigned char) ((v >> 8) & 0xff);
+        p[2] = (unsigned char) ((v >> 16) & 0xff);
+    }
+}
+
 R8B_HD double src_read_f(const SrcView& v, int ch, long long n)
 {
     if (n >= v.avail) return 0.0;
-    if (n >= v.cur_base) return R8B_LDG(v.cur + (long long) ch * v.cur_stride + (n - v.cur_base));
+    if (n >= v.cur_base) {
+        if (v.cur_fmt != FMT_F64) return typed_load(v.cur, (long long) ch * v.cur_stride + (n - v.cur_base), v.cur_fmt, v.cur_scale);
+        return R8B_LDG(v.cur + (long long) ch * v.cur_stride + (n - v.cur_base));
+    }
     return R8B_LDG(v.ring + (long long) ch * v.ring_stride + (n & v.ring_mask));
 }
 

@@ -17,6 +17,7 @@
 #include <climits>
 
 #include "r8b_fft.cuh"
+#include "r8b_fused_common.cuh"
 #include "r8b_interp.cuh"
 #include "r8b_hbfuse.cuh"
 
@@ -485,24 +486,24 @@ void launch_hbdown_cascade(const HbDownCascParams& p, int smem_bytes, const SrcV
 __global__ void __launch_bounds__(256) k_save_tail(const double* __restrict__ cur, long long cur_stride,
                                                    long long cur_base, long long n0, long long n1,
                                                    double* __restrict__ ring, long long ring_stride,
-                                                   long long ring_mask)
+                                                   long long ring_mask, int fmt, double scale)
 {
     const long long n = n0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n1) return;
     const int ch = blockIdx.y;
-    ring[(long long) ch * ring_stride + (n & ring_mask)] = cur[(long long) ch * cur_stride + (n - cur_base)];
+    const long long i = (long long) ch * cur_stride + (n - cur_base);
+    ring[(long long) ch * ring_stride + (n & ring_mask)] = fmt == FMT_F64 ? cur[i] : typed_load(cur, i, fmt, scale);
 }
 
 void launch_save_tail(const double* cur, long long cur_stride, long long cur_base, long long n0,
                       long long n1, double* ring, long long ring_stride, long long ring_mask, int n_ch,
-                      cudaStream_t st)
+                      cudaStream_t st, int fmt, double scale)
 {
     const long long n = n1 - n0;
     if (n <= 0 || n_ch <= 0) return;
     dim3 grid((unsigned) ((n + 255) / 256), (unsigned) n_ch);
-    k_save_tail<<<grid, 256, 0, st>>>(cur, cur_stride, cur_base, n0, n1, ring, ring_stride, ring_mask);
+    k_save_tail<<<grid, 256, 0, st>>>(cur, cur_stride, cur_base, n0, n1, ring, ring_stride, ring_mask, fmt, scale);
 }
-
 
 // ------------------------------------------------------------------------------------------
 // Fused cascade of half-band 2x upsamplers (CDSPHBUpsampler chain of e.g. 44100 -> 2822400,

@@ -26,6 +26,9 @@ inline void ensure_dyn_smem(int bytes)
     if (dev >= 0 && dev < 256) done[dev >> 6].fetch_or(1ull << (dev & 63), std::memory_order_release);
 }
 
+// caller-side sample formats (values of r8bgpu_sample_format, include/r8bgpu.h)
+enum { FMT_F64 = 0, FMT_F32 = 1, FMT_S16 = 2, FMT_S24 = 3, FMT_S32 = 4 };
+
 // A per-channel sample stream addressed by ABSOLUTE sample index n (n = 0 is the first sample
 // after clear()).  Samples with n >= cur_base are read from the caller's block of this
 // process() call; older samples come from a power-of-two ring that holds the recent past.
@@ -38,6 +41,12 @@ struct SrcView {
     long long cur_stride;
     long long cur_base;    // absolute index of cur[0]; LLONG_MAX when there is no cur block
     long long avail;       // samples with n >= avail do not exist yet (read as 0)
+    // Caller-side sample format of the cur block (FMT_*; FMT_F64 = plain doubles).  Only the v2 fused kernel and the
+    // history copy read typed blocks: cur then points at planar samples of that format, cur_stride counts samples, and
+    // a value is (double) sample * cur_scale -- the conversion of CDSPResampler::oneshot<Tin,Tout>()
+    // (CDSPResampler.h:592-651) done in the gather instead of in a kernel of its own.
+    int cur_fmt = 0;
+    double cur_scale = 1.0;
 };
 
 // Destination stream: either a ring (mask = capacity-1, base = 0) or a linear block whose
@@ -47,6 +56,10 @@ struct DstView {
     long long stride;
     long long mask;
     long long base;
+    // Sample format of a LINEAR destination (the v2 fused kernel's tensor-path stores only): ptr then addresses planar
+    // samples of that format, stride counts samples, and a stored value is (T) (y * scale).
+    int fmt = 0;
+    double scale = 1.0;
 };
 
 struct BlockConvParams {
@@ -204,10 +217,9 @@ void launch_hbdown(const HbParams& p, const SrcView& src, const DstView& dst, in
 // copy cur[n0..n1) into the ring (history for later calls)
 void launch_save_tail(const double* cur, long long cur_stride, long long cur_base, long long n0,
                       long long n1, double* ring, long long ring_stride, long long ring_mask, int n_ch,
-                      cudaStream_t st);
+                      cudaStream_t st, int fmt = 0, double scale = 1.0);
 
 // Caller-side sample formats (r8b_format.cu); values match r8bgpu_sample_format in include/r8bgpu.h.
-enum { FMT_F64 = 0, FMT_F32 = 1, FMT_S16 = 2, FMT_S24 = 3, FMT_S32 = 4 };
 __host__ __device__ int format_bytes(int fmt); // 0: unknown format
 // raw (any format; planar: channel c at c*raw_stride, interleaved: frame f at f*raw_stride) <-> planar fp64
 bool launch_to_f64(int fmt, const void* raw, bool interleaved, size_t raw_stride, double* f64, size_t f64_stride,

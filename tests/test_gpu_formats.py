@@ -137,3 +137,47 @@ def test_passthrough_and_errors(pkg):
     with pytest.raises(pkg.R8bGpuError):   # interleaved stride below the channel count
         a.batch.process_fmt(pkg.Buffer.make(x.ctypes.data, pkg.S16, True, 1), 256,
                             pkg.Buffer.make(x.ctypes.data, pkg.S16, False, 256), 256, host=True)
+
+
+def test_planar_formats_are_converted_inside_the_resampling_kernels(pkg):
+    """Planar typed buffers need no conversion kernels on the chains whose first / last kernel is the fused one: the
+    gather widens, the tensor-path stores narrow.  Launches per call: fused kernel + history copy (2), where the
+    interleaved layout adds the two transposing conversion kernels (4).  Results equal the separate-kernel path
+    bit for bit (R8BGPU_NO_FORMAT_FUSION) -- ragged calls included (history ring filled from typed blocks)."""
+    import os
+    src, dst, n_ch, lens = 44100.0, 96000.0, 5, [4096, 777, 4096, 1, 4096]
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-0.9, 0.9, size=(n_ch, sum(lens))).astype(np.float32)
+    outs = {}
+    for mode in ("fused", "separate"):
+        if mode == "separate":
+            os.environ["R8BGPU_NO_FORMAT_FUSION"] = "1"
+        try:
+            rb = pkg.ResamplerBatch(n_ch, src, dst, 4096, device=0)
+            pos, ys, per_call = 0, [], []
+            for l in lens:
+                l0 = rb.batch.kernel_launches
+                ys.append(rb.batch.process_host_fmt(x[:, pos:pos + l], out_dtype=np.int32, out_scale=2.0 ** 30))
+                per_call.append(rb.batch.kernel_launches - l0)
+                pos += l
+            outs[mode] = (np.concatenate(ys, axis=1), per_call)
+        finally:
+            os.environ.pop("R8BGPU_NO_FORMAT_FUSION", None)
+    assert np.array_equal(outs["fused"][0], outs["separate"][0])
+    assert max(outs["fused"][1]) == 2 and max(outs["separate"][1]) == 4, (outs["fused"][1], outs["separate"][1])
+
+
+@pytest.mark.parametrize("src,dst", [(192000.0, 44100.0), (96000.0, 44100.0), (44100.0, 88200.0)])
+def test_typed_io_on_other_fused_chains(pkg, ref, src, dst):
+    # decimating chain (typed output from the 1x fused pair), 1x pair first (typed gather), lone 2x block convolver
+    n_ch, lens = 3, [8192, 8192, 100, 8192]
+    x = pcm16(n_ch, sum(lens), 8)
+    a = pkg.ResamplerBatch(n_ch, src, dst, 8192, device=0)
+    b = pkg.ResamplerBatch(n_ch, src, dst, 8192, device=0)
+    pos = 0
+    for l in lens:
+        blk = x[:, pos:pos + l]
+        got = a.batch.process_host_fmt(blk, out_dtype=np.float32)
+        want = b.process(blk.astype(np.float64))
+        assert np.array_equal(got, c_cast(want, np.float32))
+        pos += l
