@@ -23,6 +23,14 @@
 
 #include "r8b_fused2_core.cuh"
 
+// experiment knobs of the tensor-path interpolation loop: units in flight per warp, unrolled K loop
+#ifndef R8B_F2_PAIR
+#define R8B_F2_PAIR 0
+#endif
+#ifndef R8B_F2_KUNROLL
+#define R8B_F2_KUNROLL 0
+#endif
+
 namespace r8bgpu {
 
 namespace {
@@ -294,28 +302,51 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
                 mt.load(si);
                 const int n_mu = mt.n_j > 0 ? mma_units(p, mt.c_cnt) : 0, ksteps = p.smaxp >> 2;
                 double* const so = s_o[h];
-                MmaUnit mu;
-                mu.set(wh, n_groups);
-                for (int unit = wh; unit < n_mu; unit += HT / 32, mu.advance(HT / 32, n_groups)) {
-                    const int goff = s_goff[mu.g];
-                    int yo[MBU];
+                // NQ units in flight per warp (different phase groups)
+                constexpr int NQ = R8B_F2_PAIR ? 2 : 1, WS = HT / 32;
+                MmaUnit mu[NQ];
 #pragma unroll
-                    for (int i = 0; i < MBU; i++) yo[i] = mma_a_index(p, mt, mu, goff, i, lane);
-                    const double* gb = sbank + mma_b_index(p, mu, lane);
-                    double acc[MBU][2];
+                for (int q = 0; q < NQ; q++) mu[q].set(wh + q * WS, n_groups);
+                for (int unit = wh; unit < n_mu; unit += NQ * WS) {
+                    int yo[NQ][MBU];
+                    const double* gb[NQ];
+                    double acc[NQ][MBU][2];
 #pragma unroll
-                    for (int i = 0; i < MBU; i++) acc[i][0] = acc[i][1] = 0.0;
-#pragma unroll 4
-                    for (int ks = 0; ks < ksteps; ks++) {
-                        const double b = gb[ks * 32];
+                    for (int q = 0; q < NQ; q++) {
+                        const int goff = s_goff[mu[q].g];
 #pragma unroll
                         for (int i = 0; i < MBU; i++) {
-                            const int yi = yo[i] + 4 * ks;
-                            dmma884(acc[i][0], acc[i][1], PADV ? yb[ylay(yi, p.ysh)] : yb[yi], b);
+                            yo[q][i] = mma_a_index(p, mt, mu[q], goff, i, lane);
+                            acc[q][i][0] = acc[q][i][1] = 0.0;
                         }
+                        gb[q] = sbank + mma_b_index(p, mu[q], lane);
+                    }
+                    auto kstep = [&](int ks) {
+#pragma unroll
+                        for (int q = 0; q < NQ; q++) {
+                            const double bq = gb[q][ks * 32];
+#pragma unroll
+                            for (int i = 0; i < MBU; i++) {
+                                const int yi = yo[q][i] + 4 * ks;
+                                dmma884(acc[q][i][0], acc[q][i][1], PADV ? yb[ylay(yi, p.ysh)] : yb[yi], bq);
+                            }
+                        }
+                    };
+                    if (R8B_F2_KUNROLL && ksteps == 8) { // 24..28-tap banks padded to 32: the common case, fully unrolled
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++) kstep(ks);
+                    } else {
+#pragma unroll 4
+                        for (int ks = 0; ks < ksteps; ks++) kstep(ks);
                     }
 #pragma unroll
-                    for (int i = 0; i < MBU; i++) mma_store(p, dst, t.ch, mt, so, mu, i, lane, acc[i][0], acc[i][1]);
+                    for (int q = 0; q < NQ; q++) {
+                        if (unit + q * WS < n_mu) {
+#pragma unroll
+                            for (int i = 0; i < MBU; i++) mma_store(p, dst, t.ch, mt, so, mu[q], i, lane, acc[q][i][0], acc[q][i][1]);
+                        }
+                        mu[q].advance(NQ * WS, n_groups);
+                    }
                 }
             } else if (si[0] > 0) {
                 const int n_tasks = TaskGeom<IRV, GLOG>::n_tasks(p, si[1]);

@@ -179,12 +179,25 @@ template <bool PADV>
 R8B_HD void y_store(double2* __restrict__ buf, const double2 (&v)[16], int g, long long w, int ysh)
 {
     double* yb = reinterpret_cast<double*>(buf);
-    const bool head = w < 0; // only the first tile of a stream reaches before sample 0 (tile-uniform)
+    if (w < 0) { // only the first tile of a stream reaches before sample 0 (tile-uniform branch)
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int e = g + j * 256;              // local input-rate position
+            double2 x = v[bitrev<16>(j)];
+            if (w + e < 0) x = make_double2(0.0, 0.0); // the reference's interpolator starts from silence
+            if (!PADV) {
+                reinterpret_cast<double2*>(yb)[e] = x;
+            } else {
+                yb[ylay(2 * e, ysh)] = x.x;
+                yb[ylay(2 * e + 1, ysh)] = x.y;
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        const int e = g + j * 256;              // local input-rate position
-        double2 x = v[bitrev<16>(j)];
-        if (head && w + e < 0) x = make_double2(0.0, 0.0); // the reference's interpolator starts from silence
+        const int e = g + j * 256;
+        const double2 x = v[bitrev<16>(j)];
         if (!PADV) {
             reinterpret_cast<double2*>(yb)[e] = x;
         } else {

@@ -8,9 +8,17 @@
 
 namespace r8bgpu {
 
+// (the typed paths are kept out of line: inlined into the fused kernel they cost the fp64 path ~3 % through code size and
+// register pressure, and they are not the hot case)
+#ifdef __CUDA_ARCH__
+#define R8B_HD_COLD __host__ __device__ __noinline__
+#else
+#define R8B_HD_COLD inline
+#endif
+
 // One sample of a planar typed block, widened exactly ((double) of the stored value) and scaled with a correctly
 // rounded multiply -- bit for bit what k_cvt_planar (r8b_format.cu) produces.
-R8B_HD double typed_load(const void* base, long long idx, int fmt, double scale)
+R8B_HD_COLD double typed_load(const void* base, long long idx, int fmt, double scale)
 {
     double x;
     switch (fmt) {
@@ -32,7 +40,7 @@ R8B_HD double typed_load(const void* base, long long idx, int fmt, double scale)
 }
 
 // (T) (y * scale): float rounds to nearest, integers truncate toward zero and saturate, NaN -> 0 (r8b_format.cu)
-R8B_HD void typed_store(void* base, long long idx, int fmt, double scale, double y)
+R8B_HD_COLD void typed_store(void* base, long long idx, int fmt, double scale, double y)
 {
 #ifdef __CUDA_ARCH__
     y = __dmul_rn(y, scale);
