@@ -355,13 +355,34 @@ __global__ void __launch_bounds__(256) k_hbdown(HbParams p, SrcView src, DstView
     // s_odd[i] = x[2*(m0 - T + i) + 1], i < cnt + 2T - 1 ; s_even[i] = x[2*(m0 + i)], i < cnt
     const long long n0 = 2 * (m0 - T) + 1;
     const int n_in = 2 * (cnt + 2 * T - 1) - 1;
-    for (int i = tid; i < n_in; i += 256) {
-        const double x = src_read(src, ch, n0 + i);
-        if (i & 1) {
-            const int e = (i + 1) / 2 - T; // n0+i = 2*(m0-T) + i+1
-            if (e >= 0 && e < cnt) s_even[e] = x;
-        } else {
-            s_odd[i >> 1] = x;
+    // Fast path: the whole window lies in one contiguous, 16-byte aligned run (the caller's block, or the ring without a
+    // wrap): sample pairs (x[2j], x[2j+1]) arrive as one 128-bit load and split straight into the two arrays.
+    const long long j0 = m0 - T, j1 = m0 + cnt + T - 1; // pairs j0 .. j1-1
+    const double* run = nullptr;
+    if (2 * j0 >= src.cur_base && 2 * j1 <= src.avail) {
+        run = src.cur + (long long) ch * src.cur_stride + (2 * j0 - src.cur_base);
+    } else if (j0 >= 0 && 2 * j1 <= src.avail && 2 * j1 <= src.cur_base) {
+        const long long i0 = (2 * j0) & src.ring_mask;
+        if (i0 + 2 * (j1 - j0) <= src.ring_mask + 1) run = src.ring + (long long) ch * src.ring_stride + i0;
+    }
+    if (run != nullptr && (reinterpret_cast<unsigned long long>(run) & 15) == 0) {
+        const double2* __restrict__ r2 = reinterpret_cast<const double2*>(run);
+        const int np = (int) (j1 - j0);
+        for (int i = tid; i < np; i += 256) {
+            const double2 v = __ldg(r2 + i);
+            s_odd[i] = v.y;
+            const int e = i - T;
+            if (e >= 0 && e < cnt) s_even[e] = v.x;
+        }
+    } else {
+        for (int i = tid; i < n_in; i += 256) {
+            const double x = src_read(src, ch, n0 + i);
+            if (i & 1) {
+                const int e = (i + 1) / 2 - T; // n0+i = 2*(m0-T) + i+1
+                if (e >= 0 && e < cnt) s_even[e] = x;
+            } else {
+                s_odd[i >> 1] = x;
+            }
         }
     }
     __syncthreads();
@@ -411,13 +432,44 @@ __global__ void __launch_bounds__(HBDC_NT) k_hbdown_cascade(const __grid_constan
         // first even / odd index >= lo
         const long long lo_e = lo + (lo & 1), lo_o = lo + 1 - (lo & 1);
         const int cnt = (int) (hi - lo);
-        const bool fast = lo >= src.cur_base && hi <= src.avail;
-        const double* __restrict__ a = fast ? src.cur + (long long) ch * src.cur_stride + (lo - src.cur_base) : nullptr;
-        for (int i = tid; i < cnt; i += HBDC_NT) {
-            const long long idx = lo + i;
-            const double x = fast ? __ldg(a + i) : src_read(src, ch, idx);
-            if (idx & 1) O[(idx - lo_o) >> 1] = x;
-            else E[(idx - lo_e) >> 1] = x;
+        // contiguous run holding [lo, hi): the caller's block, or the ring without a wrap
+        const double* run = nullptr;
+        if (lo >= src.cur_base && hi <= src.avail) {
+            run = src.cur + (long long) ch * src.cur_stride + (lo - src.cur_base);
+        } else if (lo >= 0 && hi <= src.avail && hi <= src.cur_base) {
+            const long long i0 = lo & src.ring_mask;
+            if (i0 + cnt <= src.ring_mask + 1) run = src.ring + (long long) ch * src.ring_stride + i0;
+        }
+        if (run != nullptr) {
+            // 128-bit loads of (even, odd) pairs from the first even index on; the odd sample in front of it, if any, alone
+            const int lead = (int) (lo_e - lo); // 0 or 1
+            if (lead && tid == 0) O[0] = __ldg(run);
+            const double* a = run + lead;
+            const int np = (cnt - lead) >> 1;
+            const int oo = (int) ((lo_e + 1 - lo_o) >> 1); // O index of the odd sample of pair 0
+            if ((reinterpret_cast<unsigned long long>(a) & 15) == 0) {
+                const double2* __restrict__ a2 = reinterpret_cast<const double2*>(a);
+#pragma unroll 4
+                for (int i = tid; i < np; i += HBDC_NT) {
+                    const double2 v = __ldg(a2 + i);
+                    E[i] = v.x;
+                    O[oo + i] = v.y;
+                }
+            } else {
+#pragma unroll 4
+                for (int i = tid; i < np; i += HBDC_NT) {
+                    E[i] = __ldg(a + 2 * i);
+                    O[oo + i] = __ldg(a + 2 * i + 1);
+                }
+            }
+            if (((cnt - lead) & 1) && tid == 0) E[np] = __ldg(a + 2 * np); // a trailing even sample
+        } else {
+            for (int i = tid; i < cnt; i += HBDC_NT) {
+                const long long idx = lo + i;
+                const double x = src_read(src, ch, idx);
+                if (idx & 1) O[(idx - lo_o) >> 1] = x;
+                else E[(idx - lo_e) >> 1] = x;
+            }
         }
     }
     __syncthreads();
