@@ -121,6 +121,7 @@ struct StageDev {
     // v2 fused kernel (r8b_fused2.cu): [q][r] twiddle tables for the bulk copy; on the BLOCKCONV stage
     double2* tw_tab = nullptr;
     double2* c_tab = nullptr;   // v2 fused kernel: phase C operands in thread order
+    double2* c_tab_v1 = nullptr; // round-1 fused kernel: its two spectrum values per frequency pair in thread order
     bool bank_frag_order = false; // grouped bank stored in mma fragment order (only the tensor-path interpolation reads it)
     bool f2_ok = false;
     bool f2_copy = false; // BlockConvolver 2/1 alone on the v2 kernel (phase E copies the 2x stream out)
@@ -205,6 +206,7 @@ struct r8bgpu_batch {
             cudaFree(d.tw);
             cudaFree(d.tw_tab);
             cudaFree(d.c_tab);
+            cudaFree(d.c_tab_v1);
             cudaFree(d.bank);
             cudaFree(d.ring);
             cudaFree(d.phase_off);
@@ -567,6 +569,11 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 const std::vector<double2> ctb = build_c_tab(spec, tw, d.fgeom.up);
                 if (!cuda_ok(cudaMalloc(&d.c_tab, ctb.size() * sizeof(double2)), "cudaMalloc(c_tab)")) return nullptr;
                 if (!cuda_ok(cudaMemcpy(d.c_tab, ctb.data(), ctb.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy c_tab")) return nullptr;
+                if (d.fused_with_next && d.fgeom.up == 2) {
+                    const std::vector<double2> c1 = build_c_tab_v1(spec);
+                    if (!cuda_ok(cudaMalloc(&d.c_tab_v1, c1.size() * sizeof(double2)), "cudaMalloc(c_tab_v1)")) return nullptr;
+                    if (!cuda_ok(cudaMemcpy(d.c_tab_v1, c1.data(), c1.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy c_tab_v1")) return nullptr;
+                }
             }
         } else if (s.kind == ST_FRAC_WHOLE || s.kind == ST_FRAC_POLY) {
             const size_t nb = s.bank.table.size() * sizeof(double);
@@ -1079,6 +1086,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.glog = fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
                 launch_up2_frac2(p, src, dst, b->n_sm, st);
             } else {
+                p.c_tab = d.c_tab_v1;
                 launch_up2_frac(p, src, dst, nch, st);
             }
             b->launches++;

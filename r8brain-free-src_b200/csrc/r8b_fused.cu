@@ -62,12 +62,9 @@ __device__ __forceinline__ void fwd_pass1_regs(double2 (&v)[16], double2* __rest
                                                const double2* __restrict__ twf, int r)
 {
     Network<16, +1>::run(v);
-#pragma unroll
-    for (int q = 0; q < 16; q++) {
-        double2 x = v[bitrev<16>(q)];
-        if (q > 0) x = cmul<+1>(x, tw_pair(twc, twf, r, q));
-        s[fft_pad(r + q * 256)] = x;
-    }
+    s[fft_pad(r)] = v[0];
+    twiddles16([&](int q) { return tw_pair(twc, twf, r, q); },
+               [&](int q, double2 w) { s[fft_pad(r + q * 256)] = cmul<+1>(v[bitrev<16>(q)], w); });
 }
 
 // Pair-level bookkeeping for the whole-stepping interpolation, done by ONE thread at kernel start (it
@@ -596,8 +593,13 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
             const int s2 = slot_of<FM>((FM - k) & (FM - 1));
             s1v[u] = s1;
             s2v[u] = s2;
-            g1[u] = __ldg(&p.spec[s1]);
-            g2[u] = __ldg(&p.spec[s2]);
+            if (p.c_tab != nullptr) { // thread-ordered copy of the two spectrum values: a warp's loads are 512 contiguous bytes
+                g1[u] = __ldg(&p.c_tab[(2 * u) * FNT + tid]);
+                g2[u] = __ldg(&p.c_tab[(2 * u + 1) * FNT + tid]);
+            } else {
+                g1[u] = __ldg(&p.spec[s1]);
+                g2[u] = __ldg(&p.spec[s2]);
+            }
         }
         auto do_pair = [&](int s1, int s2, double2 ga, double2 gb) {
             const double2 z1 = bufA[fft_pad(s1)];
@@ -634,12 +636,9 @@ __global__ void __launch_bounds__(FNT, 1) k_up2_frac(FusedParams p, SrcView src,
         R8B_TICK(5)
         // last pass: NCUR = M, D = 256, twiddle W_M^(r q) conj; results leave in y layout
         double2 v[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            double2 x = buf[fft_pad(g + q * 256)];
-            if (q > 0) x = cmul<-1>(x, tw_pair(twc, twf, g, q));
-            v[q] = x;
-        }
+        v[0] = buf[fft_pad(g)];
+        twiddles16([&](int q) { return tw_pair(twc, twf, g, q); },
+                   [&](int q, double2 w) { v[q] = cmul<-1>(buf[fft_pad(g + q * 256)], w); });
         Network<16, -1>::run(v);
         __syncthreads();
         double* yb = reinterpret_cast<double*>(buf);

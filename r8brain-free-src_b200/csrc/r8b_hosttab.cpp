@@ -131,6 +131,21 @@ std::vector<double2> build_c_tab(const std::vector<double2>& spec, const std::ve
     return ct;
 }
 
+std::vector<double2> build_c_tab_v1(const std::vector<double2>& spec)
+{
+    constexpr int NT = 512, NC = FM / (2 * NT);
+    std::vector<double2> ct((size_t) NC * 2 * NT);
+    for (int u = 0; u < NC; u++)
+        for (int tid = 0; tid < NT; tid++) {
+            const int s1 = 16 * ((tid >> 3) + 64 * u) + (tid & 7);
+            const int k = freq_of<FM>(s1);
+            const int s2 = slot_of<FM>((FM - k) & (FM - 1));
+            ct[(size_t) (2 * u) * NT + tid] = spec[(size_t) s1];
+            ct[(size_t) (2 * u + 1) * NT + tid] = spec[(size_t) s2];
+        }
+    return ct;
+}
+
 FusedGeom fused_geometry(const StageDesc& s, const StageDesc& f)
 {
     FusedGeom g;

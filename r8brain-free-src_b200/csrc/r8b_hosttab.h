@@ -40,6 +40,10 @@ struct GroupBank {
     std::vector<int> off, row; // per phase: window offset, bank row
 };
 int choose_group_ir(const StageDesc& frac);
+// the same for the round-1 fused kernel (tile pairs, 512 threads): [u < 4][item < 2][tid < 512] = spectrum at the slot
+// s1 = 16*((tid>>3) + 64u) + (tid&7) and at the slot of the mirrored frequency
+std::vector<double2> build_c_tab_v1(const std::vector<double2>& spec_slots4096);
+
 // frag_order (ir == 8 only): within every block of 4 taps the 32 values are stored as [phase][tap % 4] -- the B-fragment
 // order of mma.sync m8n8k4, so a warp's load of one K-step is 256 contiguous bytes
 GroupBank build_group_bank(const StageDesc& frac, int ir, bool frag_order = false);
