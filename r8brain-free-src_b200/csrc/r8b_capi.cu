@@ -121,6 +121,7 @@ struct StageDev {
     // v2 fused kernel (r8b_fused2.cu): [q][r] twiddle tables for the bulk copy; on the BLOCKCONV stage
     double2* tw_tab = nullptr;
     double2* c_tab = nullptr;   // v2 fused kernel: phase C operands in thread order
+    double2* cd_tab = nullptr;   // v2 fused kernel, up 2: operands of phase C fused into the first inverse pass
     double2* c_tab_v1 = nullptr; // round-1 fused kernel: its two spectrum values per frequency pair in thread order
     bool bank_frag_order = false; // grouped bank stored in mma fragment order (only the tensor-path interpolation reads it)
     bool f2_ok = false;
@@ -207,6 +208,7 @@ struct r8bgpu_batch {
             cudaFree(d.tw_tab);
             cudaFree(d.c_tab);
             cudaFree(d.c_tab_v1);
+            cudaFree(d.cd_tab);
             cudaFree(d.bank);
             cudaFree(d.ring);
             cudaFree(d.phase_off);
@@ -569,6 +571,11 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                 const std::vector<double2> ctb = build_c_tab(spec, tw, d.fgeom.up);
                 if (!cuda_ok(cudaMalloc(&d.c_tab, ctb.size() * sizeof(double2)), "cudaMalloc(c_tab)")) return nullptr;
                 if (!cuda_ok(cudaMemcpy(d.c_tab, ctb.data(), ctb.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy c_tab")) return nullptr;
+                if (d.fgeom.up == 2) {
+                    const std::vector<double2> cd = build_cd_tab(spec, tw);
+                    if (!cuda_ok(cudaMalloc(&d.cd_tab, cd.size() * sizeof(double2)), "cudaMalloc(cd_tab)")) return nullptr;
+                    if (!cuda_ok(cudaMemcpy(d.cd_tab, cd.data(), cd.size() * sizeof(double2), cudaMemcpyHostToDevice), "copy cd_tab")) return nullptr;
+                }
                 if (d.fused_with_next && d.fgeom.up == 2) {
                     const std::vector<double2> c1 = build_c_tab_v1(spec);
                     if (!cuda_ok(cudaMalloc(&d.c_tab_v1, c1.size() * sizeof(double2)), "cudaMalloc(c_tab_v1)")) return nullptr;
@@ -1078,6 +1085,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.flags = b->f2_flags;
                 p.tw_tab = d.tw_tab;
                 p.c_tab = d.c_tab;
+                p.cd_tab = d.cd_tab;
                 p.up = d.fgeom.up;
                 p.ylen = d.fgeom.up * 4096;
                 if (!fd.bank_frag_order) p.flags &= ~4; // (the bank layout decides: see batch_create)
@@ -1108,6 +1116,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 fp.tw = d.tw;
                 fp.tw_tab = d.tw_tab;
                 fp.c_tab = d.c_tab;
+                fp.cd_tab = d.cd_tab;
                 fp.up = 2;
                 fp.ylen = 8192;
                 fp.ir = 8;

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
                                                       const __grid_constant__ DstView dst)
 {
     extern __shared__ __align__(128) double2 smem[];
-    double2* const tw2 = smem + 2 * FPL;          // tw2t[q*16+r] = W_256^(r q)
+    double2* const tw2 = smem + 2 * FPL2;         // tw2t[q*16+r] = W_256^(r q)
     double2* const twf = tw2 + 256;               // tw1t[q*16+r] = W_M^(r q)
     double* const sbank = reinterpret_cast<double*>(twf + 256);
     __shared__ __align__(8) unsigned long long mb[5]; // 0: tables, 1-2: input tile of half h, 3-4: interpolation turn of half h
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
     __shared__ int s_goff[192];
 
     const int tid = threadIdx.x, h = tid >> 8, ht = tid & (HT - 1), lane = tid & 31, wh = ht >> 5;
-    double2* const buf = smem + h * FPL;
+    double2* const buf = smem + h * FPL2;
     const int n_units = p.n_tiles * p.n_ch;
     const int n_groups = (p.out_step + IRV - 1) / IRV, esz = p.smaxp * IRV;
     const bool pingpong = (p.flags & 1) != 0, tma_in = (p.flags & 2) != 0;
@@ -225,33 +225,33 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
         if (!COPY && ht == HT - 1) interp_prepare(p, dst, t, s_i[h], &s_o[h]);
         bar_half(h);
         // B. the two radix-16 passes act on 256-point blocks owned by one half-warp each
+        constexpr bool fuse_c = (UP == 2); // the 1x pair keeps its separate split pass
         if (ht < FN / 16) {
             fwd_pass<256>(buf, tw2, ht);
             __syncwarp();
-            fwd_pass<16>(buf, tw2, ht);
+            if constexpr (fuse_c) fwd_pass16_skew(buf, ht);
+            else fwd_pass<16>(buf, tw2, ht);
         }
         bar_half(h);
-        // C. split + multiply by the filter spectrum, in place (all loads before the first store)
-        {
+        // C. split + multiply by the filter spectrum -- fused into the first inverse pass (UP == 2), or in place
+        if constexpr (fuse_c) {
+            double2 z1[8], z2[8];
+            cd1_load(buf, ht, z1, z2);
+            bar_half(h);
+            cd1_compute(p, buf, ht, z1, z2);
+        } else {
             double2 z1[4], z2[4], ze = make_double2(0.0, 0.0);
             c_load(buf, ht, z1, z2);
             if (ht == 0) ze = buf[fft_pad(slot_of<FN>(FN / 2))];
             bar_half(h);
-            if constexpr (UP == 2) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) c_pair_tab(p, buf, ht, i, z1[i], z2[i]);
-                if (ht == 0) c_pair(p, buf, FN / 2, ze, ze);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; i++) c1_pair_tab(p, buf, ht, i, z1[i], z2[i]);
-                if (ht == 0) c1_pair_mid(p, buf, ze);
-            }
+            for (int i = 0; i < 4; i++) c1_pair_tab(p, buf, ht, i, z1[i], z2[i]);
+            if (ht == 0) c1_pair_mid(p, buf, ze);
+            bar_half(h);
         }
-        bar_half(h);
         // D. inverse transform
         if constexpr (UP == 2) {
-            inv_pass<16>(buf, tw2, ht);
-            __syncwarp();
+            __syncwarp(); // the first inverse pass ran inside phase C (cd1_compute)
             inv_pass<256>(buf, tw2, ht);
             bar_half(h);
             {
@@ -382,10 +382,10 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
 
 int fused2_smem_bytes(int bank_doubles, bool staged)
 {
-    return 2 * FPL * (int) sizeof(double2) + 512 * (int) sizeof(double2) + ((bank_doubles + 1) & ~1) * (int) sizeof(double) +
+    return 2 * FPL2 * (int) sizeof(double2) + 512 * (int) sizeof(double2) + ((bank_doubles + 1) & ~1) * (int) sizeof(double) +
            (staged ? (NT2 / 32) * 256 * (int) sizeof(double) : 0);
 }
-int fused2_stage_off(int bank_doubles) { return 2 * (2 * FPL + 512) + ((bank_doubles + 1) & ~1); }
+int fused2_stage_off(int bank_doubles) { return 2 * (2 * FPL2 + 512) + ((bank_doubles + 1) & ~1); }
 
 template <int IRV, bool PADV, int GLOG, bool TC = false, int UP = 2, bool COPY = false>
 static void launch_inst2(const FusedParams& p, const SrcView& src, const DstView& dst, int grid, int smem, cudaStream_t st)

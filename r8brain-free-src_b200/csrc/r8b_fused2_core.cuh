@@ -23,6 +23,8 @@ namespace r8bgpu {
 namespace f2 {
 
 constexpr int FN = 2048;   // complex length of the forward transform (real length FM = 4096)
+constexpr int FPL2 = FPL + 16; // double2 per tile buffer: room for the skewed copy of the forward result in its upper half
+constexpr int SKEW0 = fft_padded_len(FN); // where that copy starts (= where a bulk-copied input tile lands)
 constexpr int HT = 256;    // threads of one half-CTA pipeline
 constexpr int IQ2 = 3;     // stepping cycles per lane in the interpolation register tile
 
@@ -163,6 +165,71 @@ R8B_HD void c_pair_tab(const FusedParams& p, double2* __restrict__ buf, int ht, 
 {
     const double2* __restrict__ ct = p.c_tab + (u * 5) * HT + ht;
     c_pair_ops(buf, c_freq(ht, u), z1, z2, R8B_LDG(ct), R8B_LDG(ct + HT), R8B_LDG(ct + 2 * HT), R8B_LDG(ct + 3 * HT), R8B_LDG(ct + 4 * HT));
+}
+
+// ---- phase C fused into the first inverse pass (up-factor 2) -------------------------------------------------------
+// The first inverse pass gives butterfly g = 16 q1 + q2 the sixteen bins k = q1 + 16 q2 + 256 q3 (slots 16 g + q3).  They
+// are X[kappa_t] G and X[kappa_t + N] G for kappa_t = q1 + 16 q2 + 256 t, t < 8, and both come from the forward values
+// Z[kappa_t], Z[N - kappa_t]: a thread that fetches those sixteen values computes its own butterfly inputs, and the
+// separate split pass -- its stores, the butterfly's loads, one barrier -- disappears.  For the fetches to stay
+// conflict-free the last forward pass leaves Z in a SKEWED layout in the buffer's upper half,
+//     skew(slot) = slot + slot/16 + slot/128
+// (a quarter-warp reads blocks B0 + 2i, i < 8: the extra slot/128 term separates the two groups of four that the plain
+// slot/16 padding puts on the same banks).  W_M^kappa_t = W_M^(q1 + 16 q2) * W_16^t: one table value per thread and the
+// constant roots of the radix-16 network.  Operands in thread order (FusedParams::cd_tab): [q3 < 16][g < 256] spectrum,
+// then [g < 256] twiddles.
+R8B_HD int skew(int slot) { return slot + (slot >> 4) + (slot >> 7); }
+
+// last forward pass (16-point blocks), out of place into the skewed layout
+R8B_HD void fwd_pass16_skew(double2* __restrict__ buf, int g)
+{
+    double2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = buf[fft_pad(16 * g + j)];
+    Network<16, +1>::run(v);
+#pragma unroll
+    for (int q = 0; q < 16; q++) buf[SKEW0 + skew(16 * g + q)] = v[bitrev<16>(q)];
+}
+
+R8B_HD void cd1_load(const double2* __restrict__ buf, int g, double2 (&z1)[8], double2 (&z2)[8])
+{
+    const int k0 = (g >> 4) + 16 * (g & 15);
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const int k = k0 + 256 * t;
+        z1[t] = buf[SKEW0 + skew(slot_of<FN>(k))];
+        z2[t] = buf[SKEW0 + skew(slot_of<FN>((FN - k) & (FN - 1)))];
+    }
+}
+
+template <int T>
+R8B_HD void cd1_bin(const FusedParams& p, int g, double2 w0, double2 z1, double2 z2, double2 (&v)[16])
+{
+    const double2 a = make_double2(z1.x + z2.x, z1.y - z2.y);
+    const double2 b = make_double2(z1.y + z2.y, z2.x - z1.x);
+    const double2 wb = cmul<+1>(b, mul_root<16, T, +1>(w0));
+    const double2 x0 = make_double2(a.x + wb.x, a.y + wb.y);
+    const double2 x1 = make_double2(a.x - wb.x, a.y - wb.y);
+    v[T] = cmul<+1>(x0, R8B_LDG(&p.cd_tab[T * HT + g]));
+    v[T + 8] = cmul<+1>(x1, R8B_LDG(&p.cd_tab[(T + 8) * HT + g]));
+}
+
+// butterfly g of the first inverse pass, inputs computed from the forward values
+R8B_HD void cd1_compute(const FusedParams& p, double2* __restrict__ buf, int g, const double2 (&z1)[8], const double2 (&z2)[8])
+{
+    const double2 w0 = R8B_LDG(&p.cd_tab[16 * HT + g]);
+    double2 v[16];
+    cd1_bin<0>(p, g, w0, z1[0], z2[0], v);
+    cd1_bin<1>(p, g, w0, z1[1], z2[1], v);
+    cd1_bin<2>(p, g, w0, z1[2], z2[2], v);
+    cd1_bin<3>(p, g, w0, z1[3], z2[3], v);
+    cd1_bin<4>(p, g, w0, z1[4], z2[4], v);
+    cd1_bin<5>(p, g, w0, z1[5], z2[5], v);
+    cd1_bin<6>(p, g, w0, z1[6], z2[6], v);
+    cd1_bin<7>(p, g, w0, z1[7], z2[7], v);
+    Network<16, -1>::run(v);
+#pragma unroll
+    for (int j = 0; j < 16; j++) buf[fft_pad(16 * g + j)] = v[bitrev<16>(j)];
 }
 
 // inverse, last pass (NCUR = M, D = 256): loads + butterfly; the results leave through y_store()

@@ -131,6 +131,17 @@ std::vector<double2> build_c_tab(const std::vector<double2>& spec, const std::ve
     return ct;
 }
 
+std::vector<double2> build_cd_tab(const std::vector<double2>& spec, const std::vector<double2>& tw)
+{
+    using namespace f2;
+    std::vector<double2> ct((size_t) 17 * HT);
+    for (int g = 0; g < HT; g++) {
+        for (int q3 = 0; q3 < 16; q3++) ct[(size_t) q3 * HT + g] = spec[(size_t) (16 * g + q3)];
+        ct[(size_t) 16 * HT + g] = tw[(size_t) ((g >> 4) + 16 * (g & 15))];
+    }
+    return ct;
+}
+
 std::vector<double2> build_c_tab_v1(const std::vector<double2>& spec)
 {
     constexpr int NT = 512, NC = FM / (2 * NT);

@@ -40,6 +40,8 @@ struct GroupBank {
     std::vector<int> off, row; // per phase: window offset, bank row
 };
 int choose_group_ir(const StageDesc& frac);
+// operands of the v2 kernel's fused phase C + first inverse pass (FusedParams::cd_tab)
+std::vector<double2> build_cd_tab(const std::vector<double2>& spec_slots4096, const std::vector<double2>& tw4096);
 // the same for the round-1 fused kernel (tile pairs, 512 threads): [u < 4][item < 2][tid < 512] = spectrum at the slot
 // s1 = 16*((tid>>3) + 64u) + (tid&7) and at the slot of the mirrored frequency
 std::vector<double2> build_c_tab_v1(const std::vector<double2>& spec_slots4096);

@@ -24,7 +24,7 @@ struct Emul {
     std::vector<StageCall> calls;
     FusedGeom fg;
     GroupBank B;
-    std::vector<double2> spec, tw, tw_tab, c_tab;
+    std::vector<double2> spec, tw, tw_tab, c_tab, cd_tab;
     std::vector<double> ring; // the whole past of the input stream (power-of-two ring, zero before the start)
     long long ring_mask = 0;
     int glog_force = -1;
@@ -73,7 +73,7 @@ void interp_tc(const FusedParams& p, const DstView& dst, const Tile& t, const do
 template <int IR, bool PADV, int GLOG>
 void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, const Emul& E)
 {
-    std::vector<double2> buf((size_t) FPL);
+    std::vector<double2> buf((size_t) FPL2);
     const double2* tw2 = E.tw_tab.data();
     const double2* twf = tw2 + 256;
     const int n_groups = (p.out_step + IR - 1) / IR, esz = p.smaxp * IR;
@@ -103,8 +103,9 @@ void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, con
         double* s_o = nullptr;
         interp_prepare(p, dst, t, s_i, &s_o);
         for (int ht = 0; ht < FN / 16; ht++) fwd_pass<256>(buf.data(), tw2, ht);
-        for (int ht = 0; ht < FN / 16; ht++) fwd_pass<16>(buf.data(), tw2, ht);
-        {
+        if (p.up == 1) for (int ht = 0; ht < FN / 16; ht++) fwd_pass<16>(buf.data(), tw2, ht);
+        else for (int ht = 0; ht < FN / 16; ht++) fwd_pass16_skew(buf.data(), ht);
+        if (p.up == 1) {
             std::vector<double2> z1((size_t) HT * 4), z2((size_t) HT * 4);
             for (int ht = 0; ht < HT; ht++) {
                 double2 a[4], b[4];
@@ -115,14 +116,26 @@ void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, con
                 }
             }
             const double2 ze = buf[(size_t) fft_pad(slot_of<FN>(FN / 2))];
-            if (p.up == 1) {
-                for (int ht = 0; ht < HT; ht++)
-                    for (int i = 0; i < 4; i++) c1_pair_tab(p, buf.data(), ht, i, z1[(size_t) ht * 4 + i], z2[(size_t) ht * 4 + i]);
-                c1_pair_mid(p, buf.data(), ze);
-            } else {
-                for (int ht = 0; ht < HT; ht++)
-                    for (int i = 0; i < 4; i++) c_pair_tab(p, buf.data(), ht, i, z1[(size_t) ht * 4 + i], z2[(size_t) ht * 4 + i]);
-                c_pair(p, buf.data(), FN / 2, ze, ze);
+            for (int ht = 0; ht < HT; ht++)
+                for (int i = 0; i < 4; i++) c1_pair_tab(p, buf.data(), ht, i, z1[(size_t) ht * 4 + i], z2[(size_t) ht * 4 + i]);
+            c1_pair_mid(p, buf.data(), ze);
+        } else { // phase C inside the first inverse pass: every "thread" fetches, then (after the barrier) computes
+            std::vector<double2> z1((size_t) HT * 8), z2((size_t) HT * 8);
+            for (int ht = 0; ht < HT; ht++) {
+                double2 a[8], b[8];
+                cd1_load(buf.data(), ht, a, b);
+                for (int i = 0; i < 8; i++) {
+                    z1[(size_t) ht * 8 + i] = a[i];
+                    z2[(size_t) ht * 8 + i] = b[i];
+                }
+            }
+            for (int ht = 0; ht < HT; ht++) {
+                double2 a[8], b[8];
+                for (int i = 0; i < 8; i++) {
+                    a[i] = z1[(size_t) ht * 8 + i];
+                    b[i] = z2[(size_t) ht * 8 + i];
+                }
+                cd1_compute(p, buf.data(), ht, a, b);
             }
         }
         if (p.up == 1) {
@@ -140,7 +153,6 @@ void run_units(const FusedParams& p, const SrcView& src, const DstView& dst, con
                 y_store1<PADV>(buf.data(), a, ht, t.w, p.ysh);
             }
         } else {
-        for (int ht = 0; ht < HT; ht++) inv_pass<16>(buf.data(), tw2, ht);
         for (int ht = 0; ht < HT; ht++) inv_pass<256>(buf.data(), tw2, ht);
         {
             std::vector<double2> v((size_t) HT * 16);
@@ -208,6 +220,7 @@ void* f2emul_create(double src, double dst, int max_in_len, double tb, double at
     build_spectrum(E->plan.stages[0], 12, E->spec, E->tw, nullptr);
     E->tw_tab = build_tw_tab(E->tw);
     E->c_tab = build_c_tab(E->spec, E->tw, E->fg.up);
+    E->cd_tab = build_cd_tab(E->spec, E->tw);
     E->ring.assign((size_t) 1 << 22, 0.0);
     E->ring_mask = ((long long) 1 << 22) - 1;
     E->glog_force = E->tc ? -1 : glog_force;
@@ -236,6 +249,7 @@ int f2emul_process(void* h, const double* x, int l, double* out, int out_cap)
         p.spec = E.spec.data();
         p.tw = E.tw.data();
         p.c_tab = E.c_tab.data();
+        p.cd_tab = E.cd_tab.data();
         p.up = E.fg.up;
         p.ylen = E.fg.up * 4096;
         p.gbank = E.B.gb.data();
