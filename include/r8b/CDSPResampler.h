@@ -161,6 +161,67 @@ private:
     CDSPResamplerBatch& operator=(const CDSPResamplerBatch&);
 };
 
+/// "Pull" use of a batch for real-time callers (README.md:132-146 of the reference: "a pull method ... calls the
+/// resampling process until the output buffer is filled", keeping the excess output for the next request).  The
+/// reference leaves that loop to the caller; this helper is the same loop around CDSPResamplerBatch with host buffers:
+/// pull() asks `fill` for input blocks of at most MaxInLen frames per channel until `n` output frames per channel are
+/// available, hands them out, and keeps what is left over.  Output is exactly the push-mode stream, in the same order.
+class CDSPResamplerPull {
+public:
+    CDSPResamplerPull(const int NumChannels, const double SrcSampleRate, const double DstSampleRate, const int aMaxInLen,
+                      const double ReqTransBand = 2.0, const double ReqAtten = 206.91, const int Device = -1)
+        : Rs(NumChannels, SrcSampleRate, DstSampleRate, aMaxInLen, ReqTransBand, ReqAtten, fprLinearPhase, Device)
+        , Channels(NumChannels)
+        , MaxInLen(aMaxInLen)
+        , Cap(Rs.getMaxOutLen() > 0 ? Rs.getMaxOutLen() : 1)
+        , Have(0)
+        , In((size_t) NumChannels * (size_t) aMaxInLen)
+        , Out((size_t) NumChannels * (size_t) Cap)
+        , Fifo((size_t) NumChannels)
+    {
+    }
+
+    bool isValid() const { return Rs.isValid(); }
+    CDSPResamplerBatch& batch() { return Rs; }
+
+    /// fill(double* ip, size_t stride, int maxFrames) -> frames written per channel (planar, channel c at ip + c*stride);
+    /// returning 0 ends the stream (pull() then returns fewer than n frames).  op: planar, channel c at op + c*OutStride.
+    template <typename Fill>
+    int pull(Fill fill, double* op, const size_t OutStride, const int n)
+    {
+        while (Have < n) {
+            const int l = fill(&In[0], (size_t) MaxInLen, MaxInLen);
+            if (l <= 0) break;
+            const int got = Rs.process(&In[0], (size_t) MaxInLen, l, &Out[0], (size_t) Cap, Cap);
+            if (got < 0) return -1;
+            for (int c = 0; c < Channels; c++)
+                Fifo[(size_t) c].insert(Fifo[(size_t) c].end(), Out.begin() + (size_t) c * Cap, Out.begin() + (size_t) c * Cap + got);
+            Have += got;
+        }
+        const int give = Have < n ? Have : n;
+        for (int c = 0; c < Channels; c++) {
+            std::vector<double>& f = Fifo[(size_t) c];
+            std::copy(f.begin(), f.begin() + give, op + (size_t) c * OutStride);
+            f.erase(f.begin(), f.begin() + give);
+        }
+        Have -= give;
+        return give;
+    }
+
+    void clear()
+    {
+        Rs.clear();
+        for (size_t c = 0; c < Fifo.size(); c++) Fifo[c].clear();
+        Have = 0;
+    }
+
+private:
+    CDSPResamplerBatch Rs;
+    int Channels, MaxInLen, Cap, Have;
+    std::vector<double> In, Out;
+    std::vector<std::vector<double> > Fifo;
+};
+
 /// Single-stream object with the reference's exact call shape.
 class CDSPResampler {
 public:

@@ -34,6 +34,37 @@ int main(int argc, char** argv)
         printf("%d %d %d\n", before, (int) ok.isValid(), start);
         return 0;
     }
+    if (argc == 9 && strcmp(argv[8], "--pull") == 0) {
+        // pull mode: the same stream requested in odd-sized pieces must equal the push-mode output
+        const int n_ch = atoi(argv[3]), frames = atoi(argv[4]), block = atoi(argv[7]);
+        std::vector<double> in((size_t) n_ch * frames);
+        FILE* f = fopen(argv[1], "rb");
+        if (!f || fread(in.data(), sizeof(double), in.size(), f) != in.size()) return 3;
+        fclose(f);
+        r8b::CDSPResamplerPull rs(n_ch, atof(argv[5]), atof(argv[6]), block, 2.0, 180.15);
+        int pos = 0;
+        auto fill = [&](double* ip, size_t stride, int maxFrames) {
+            const int l = frames - pos < maxFrames ? frames - pos : maxFrames;
+            for (int c = 0; c < n_ch; c++) memcpy(ip + c * stride, &in[(size_t) c * frames + pos], sizeof(double) * (size_t) l);
+            pos += l;
+            return l;
+        };
+        std::vector<std::vector<double> > out((size_t) n_ch);
+        std::vector<double> piece((size_t) n_ch * 1000);
+        for (int req = 1;; req = req % 997 + 101) {
+            const int got = rs.pull(fill, piece.data(), 1000, req > 1000 ? 1000 : req);
+            if (got <= 0) break;
+            for (int c = 0; c < n_ch; c++) out[(size_t) c].insert(out[(size_t) c].end(), piece.begin() + c * 1000, piece.begin() + c * 1000 + got);
+        }
+        f = fopen(argv[2], "wb");
+        for (int c = 0; c < n_ch; c++) {
+            const long long n = (long long) out[(size_t) c].size();
+            fwrite(&n, sizeof n, 1, f);
+            fwrite(out[(size_t) c].data(), sizeof(double), (size_t) n, f);
+        }
+        fclose(f);
+        return 0;
+    }
     if (argc != 8) return 2;
     const int n_ch = atoi(argv[3]), frames = atoi(argv[4]), block = atoi(argv[7]);
     const double src = atof(argv[5]), dst = atof(argv[6]);

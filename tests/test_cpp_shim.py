@@ -71,6 +71,28 @@ def test_shim_process_matches_reference(pkg, ref, tmp_path):
         assert m <= 32 * ou.EPS and rr <= 4 * ou.EPS
 
 
+@pytest.mark.gpu
+def test_pull_mode_equals_push_mode(pkg, ref, tmp_path):
+    """README.md:132-146: real-time callers pull output; the helper must hand out exactly the push-mode stream."""
+    exe = build_demo(pkg)
+    n_ch, frames, block = 2, 30000, 2048
+    x = ou.white_noise(n_ch, frames, 13)
+    fin, fout = str(tmp_path / "in.f64"), str(tmp_path / "out.f64")
+    x.tofile(fin)
+    subprocess.run([exe, fin, fout, str(n_ch), str(frames), "44100", "96000", str(block), "--pull"], check=True)
+    raw = open(fout, "rb").read()
+    pos = 0
+    for c in range(n_ch):
+        n = int(np.frombuffer(raw[pos:pos + 8], dtype=np.int64)[0])
+        y = np.frombuffer(raw[pos + 8:pos + 8 + 8 * n], dtype=np.float64)
+        pos += 8 + 8 * n
+        r = ref.Resampler(44100.0, 96000.0, block, 2.0, 180.15)
+        yr = np.concatenate([r.process(x[c, i:i + block]) for i in range(0, frames, block)])
+        assert len(yr) == n
+        m, rr = ou.parity_metrics(y, yr)
+        assert m <= 32 * ou.EPS and rr <= 4 * ou.EPS
+
+
 # ---- the reference's DLL interface (DLL/r8bsrc.h): libr8bsrc.so driven from plain C -------------------------------------
 DLL_EXE = os.path.join(ROOT, "tests", "cpp", "dll_demo")
 
