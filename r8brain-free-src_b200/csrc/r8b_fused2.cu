@@ -304,8 +304,6 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
                 double* const so = s_o[h];
                 // NQ units in flight per warp (different phase groups)
                 constexpr int NQ = R8B_F2_PAIR ? 2 : 1, WS = HT / 32;
-                MmaFast mf;
-                mf.prepare(p, dst, mt, so);
                 MmaUnit mu[NQ];
 #pragma unroll
                 for (int q = 0; q < NQ; q++) mu[q].set(wh + q * WS, n_groups);
@@ -313,14 +311,12 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
                     int yo[NQ][MBU];
                     const double* gb[NQ];
                     double acc[NQ][MBU][2];
-                    bool fast[NQ];
 #pragma unroll
                     for (int q = 0; q < NQ; q++) {
                         const int goff = s_goff[mu[q].g];
-                        fast[q] = mf.unit_ok(p, mt, mu[q], goff); // warp-uniform
 #pragma unroll
                         for (int i = 0; i < MBU; i++) {
-                            yo[q][i] = fast[q] ? mma_a_index_fast(p, mt, mu[q], goff, i, lane) : mma_a_index(p, mt, mu[q], goff, i, lane);
+                            yo[q][i] = mma_a_index(p, mt, mu[q], goff, i, lane);
                             acc[q][i][0] = acc[q][i][1] = 0.0;
                         }
                         gb[q] = sbank + mma_b_index(p, mu[q], lane);
@@ -346,13 +342,8 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
 #pragma unroll
                     for (int q = 0; q < NQ; q++) {
                         if (unit + q * WS < n_mu) {
-                            if (fast[q]) {
 #pragma unroll
-                                for (int i = 0; i < MBU; i++) mma_store_fast(p, mt, so, mu[q], i, lane, acc[q][i][0], acc[q][i][1]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < MBU; i++) mma_store(p, dst, t.ch, mt, so, mu[q], i, lane, acc[q][i][0], acc[q][i][1]);
-                            }
+                            for (int i = 0; i < MBU; i++) mma_store(p, dst, t.ch, mt, so, mu[q], i, lane, acc[q][i][0], acc[q][i][1]);
                         }
                         mu[q].advance(NQ * WS, n_groups);
                     }

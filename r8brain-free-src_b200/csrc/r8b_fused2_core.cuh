@@ -578,40 +578,6 @@ R8B_HD void mma_store(const FusedParams& p, const DstView& dst, int ch, const Mm
     }
 }
 
-// Fast path of a work unit: when all MBU blocks of the unit lie strictly inside the tile (every cycle exists, every window
-// inside the stream buffer, every output inside the tile's output range and the phase row inside the stepping cycle),
-// and the destination is a plain fp64 block whose rows keep 16-byte alignment, no lane needs a predicate: the window index
-// is one multiply-add and the store one 128-bit instruction.  The test is warp-uniform arithmetic on the unit's extremes.
-struct MmaFast {
-    bool dst_ok;     // per tile: linear fp64 destination, even out_step, first output of (cycle 0, phase 0) 16-byte aligned
-    R8B_HD void prepare(const FusedParams& p, const DstView& dst, const MmaTile& mt, const double* s_o)
-    {
-        dst_ok = dst.fmt == FMT_F64 && dst.mask == -1 && (p.out_step & 1) == 0 &&
-                 (((reinterpret_cast<unsigned long long>(s_o) >> 3) + (unsigned long long) (long long) (mt.jshift + p.delta)) & 1ull) == 0;
-    }
-    R8B_HD bool unit_ok(const FusedParams& p, const MmaTile& mt, const MmaUnit& u, int goff) const
-    {
-        const int b0 = u.chunk * MBU, b1 = b0 + MBU - 1;
-        const int c_lo = mma_cycle(b0, 0), c_hi = mma_cycle(b1, 7); // rows 0 / 7 hold a block's first / last cycle
-        const int rr = p.delta + u.g * 8;
-        const int j_lo = c_lo * p.out_step + rr + mt.jshift, j_hi = c_hi * p.out_step + rr + 7 + mt.jshift;
-        const int li_lo = c_lo * p.in_step + goff + mt.wbase, li_hi = c_hi * p.in_step + goff + mt.wbase;
-        return dst_ok && c_hi <= mt.c_cnt && j_lo >= 0 && j_hi < mt.n_j && (p.wrap || rr + 8 <= p.out_step) && li_lo >= 0 &&
-               li_hi <= p.ylen - p.smaxp;
-    }
-};
-
-R8B_HD int mma_a_index_fast(const FusedParams& p, const MmaTile& mt, const MmaUnit& u, int goff, int i, int lane)
-{
-    return mma_cycle(u.chunk * MBU + i, lane >> 2) * p.in_step + goff + mt.wbase + (lane & 3);
-}
-
-R8B_HD void mma_store_fast(const FusedParams& p, const MmaTile& mt, double* s_o, const MmaUnit& u, int i, int lane, double c0, double c1)
-{
-    const int j = mma_cycle(u.chunk * MBU + i, lane >> 2) * p.out_step + p.delta + u.g * 8 + 2 * (lane & 3) + mt.jshift;
-    *reinterpret_cast<double2*>(s_o + j) = make_double2(c0, c1);
-}
-
 } // namespace f2
 
 } // namespace r8bgpu
