@@ -806,6 +806,17 @@ int r8bgpu_batch_set_stream(r8bgpu_batch* b, void* stream)
         set_err("batch_set_stream: a multi-device batch has one stream per shard (use r8bgpu_batch_shard())");
         return -1;
     }
+    if ((cudaStream_t) stream != b->stream) {
+        // work queued on the old stream (previous calls share the rings with the next ones) must be ordered before anything
+        // the new stream runs: an event recorded there, waited for here
+        DeviceGuard g(b->device);
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+            cudaEventRecord(ev, b->stream);
+            cudaStreamWaitEvent((cudaStream_t) stream, ev, 0);
+            cudaEventDestroy(ev);
+        }
+    }
     b->stream = (cudaStream_t) stream;
     return 0;
 }
@@ -1258,9 +1269,15 @@ int r8bgpu_batch_process(r8bgpu_batch* b, const double* d_in, size_t in_stride, 
         return -1;
     }
 
-    if (!upload_fasttiming(b, st)) return -1;
+    if (!upload_fasttiming(b, st)) {
+        b->sched = saved;
+        return -1;
+    }
     launch_call(b, d_in, in_stride, l, d_out, out_stride, 0, b->n_ch, st);
-    if (!cuda_ok(cudaGetLastError(), "batch_process: kernel launch")) return -1;
+    if (!cuda_ok(cudaGetLastError(), "batch_process: kernel launch")) {
+        b->sched = saved; // a refused launch did nothing: the call did not happen
+        return -1;
+    }
     return n_out;
 }
 
@@ -1367,8 +1384,17 @@ static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, co
         b->dev_bytes += o_cap * b->n_ch * 8;
     }
     int n = l;
+    const Schedule saved = b->sched;
+    // any failure after the schedule has advanced: put it back and drain the pipeline streams, so that the rings and the
+    // schedule still agree on the next call (the failed call then simply did not happen)
+    auto fail = [&]() {
+        b->sched = saved;
+        cudaStreamSynchronize(b->s_h2d);
+        cudaStreamSynchronize(b->s_comp);
+        cudaStreamSynchronize(b->s_d2h);
+        return -1;
+    };
     if (!P.passthrough) {
-        Schedule saved = b->sched;
         n = b->sched.advance(l, b->calls);
         if (n > out_cap || (n > 0 && out.data == nullptr)) {
             b->sched = saved;
@@ -1380,8 +1406,8 @@ static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, co
         return -1;
     }
     // order after any device-path work queued on the batch stream (the two paths share the rings)
-    if (!cuda_ok(cudaStreamSynchronize(b->stream), "process_host: sync(batch stream)")) return -1;
-    if (!P.passthrough && !upload_fasttiming(b, b->s_comp)) return -1;
+    if (!cuda_ok(cudaStreamSynchronize(b->stream), "process_host: sync(batch stream)")) return fail();
+    if (!P.passthrough && !upload_fasttiming(b, b->s_comp)) return fail();
     const int G = b->host_groups;
     const unsigned char* hin = (const unsigned char*) in.data;
     unsigned char* hout = (unsigned char*) out.data;
@@ -1405,7 +1431,7 @@ static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, co
             else // device copy: [nch][in_cap]
                 e = cudaMemcpy2DAsync(rin, in_cap * ein, hin + (size_t) ch0 * in.stride * ein, in.stride * ein,
                                       (size_t) l * ein, (size_t) nch, cudaMemcpyHostToDevice, b->s_h2d);
-            if (!cuda_ok(e, "process_host: H2D")) return -1;
+            if (!cuda_ok(e, "process_host: H2D")) return fail();
         }
         cudaEventRecord(b->ev_h2d[(size_t) gi], b->s_h2d);
         cudaStreamWaitEvent(b->s_comp, b->ev_h2d[(size_t) gi], 0);
@@ -1449,12 +1475,12 @@ static int process_host_impl(r8bgpu_batch* b, const r8bgpu_buffer& in, int l, co
             else
                 e = cudaMemcpy2DAsync(hout + (size_t) ch0 * out.stride * eout, out.stride * eout, rout, o_cap * eout,
                                       (size_t) n * eout, (size_t) nch, cudaMemcpyDeviceToHost, b->s_d2h);
-            if (!cuda_ok(e, "process_host: D2H")) return -1;
+            if (!cuda_ok(e, "process_host: D2H")) return fail();
         }
     }
-    if (!cuda_ok(cudaStreamSynchronize(b->s_d2h), "process_host: sync")) return -1;
-    if (!cuda_ok(cudaStreamSynchronize(b->s_comp), "process_host: sync")) return -1;
-    if (!cuda_ok(cudaGetLastError(), "process_host: kernel launch")) return -1;
+    if (!cuda_ok(cudaStreamSynchronize(b->s_d2h), "process_host: sync")) return fail();
+    if (!cuda_ok(cudaStreamSynchronize(b->s_comp), "process_host: sync")) return fail();
+    if (!cuda_ok(cudaGetLastError(), "process_host: kernel launch")) return fail();
     return n;
 }
 

@@ -65,6 +65,39 @@ int main(int argc, char** argv)
         fclose(f);
         return 0;
     }
+    if (argc == 9 && strcmp(argv[8], "--batch") == 0) {
+        // r8b::CDSPResamplerBatch with Device = -1: every visible GPU behind one object (R8BGPU_FORCE_SHARDS on one GPU),
+        // buffers from r8bgpu_batch_host_alloc (rows on the owning GPU's NUMA node)
+        const int n_ch = atoi(argv[3]), frames = atoi(argv[4]), block = atoi(argv[7]);
+        std::vector<double> in((size_t) n_ch * frames);
+        FILE* f = fopen(argv[1], "rb");
+        if (!f || fread(in.data(), sizeof(double), in.size(), f) != in.size()) return 3;
+        fclose(f);
+        r8b::CDSPResamplerBatch rs(n_ch, atof(argv[5]), atof(argv[6]), block, 2.0, 180.15);
+        const int cap = rs.getMaxOutLen();
+        double* hin = (double*) r8bgpu_batch_host_alloc(rs.handle(), (size_t) block, 8);
+        double* hout = (double*) r8bgpu_batch_host_alloc(rs.handle(), (size_t) cap, 8);
+        if (!hin || !hout) return 4;
+        std::vector<std::vector<double> > out((size_t) n_ch);
+        for (int pos = 0; pos < frames; pos += block) {
+            const int l = frames - pos < block ? frames - pos : block;
+            for (int c = 0; c < n_ch; c++) memcpy(hin + (size_t) c * block, &in[(size_t) c * frames + pos], sizeof(double) * (size_t) l);
+            const int n = rs.process(hin, (size_t) block, l, hout, (size_t) cap, cap);
+            if (n < 0) return 5;
+            for (int c = 0; c < n_ch; c++) out[(size_t) c].insert(out[(size_t) c].end(), hout + (size_t) c * cap, hout + (size_t) c * cap + n);
+        }
+        f = fopen(argv[2], "wb");
+        for (int c = 0; c < n_ch; c++) {
+            const long long n = (long long) out[(size_t) c].size();
+            fwrite(&n, sizeof n, 1, f);
+            fwrite(out[(size_t) c].data(), sizeof(double), (size_t) n, f);
+        }
+        fclose(f);
+        printf("%d\n", r8bgpu_batch_shard_count(rs.handle()));
+        r8bgpu_host_free(hin);
+        r8bgpu_host_free(hout);
+        return 0;
+    }
     if (argc != 8) return 2;
     const int n_ch = atoi(argv[3]), frames = atoi(argv[4]), block = atoi(argv[7]);
     const double src = atof(argv[5]), dst = atof(argv[6]);

@@ -93,6 +93,34 @@ def test_pull_mode_equals_push_mode(pkg, ref, tmp_path):
         assert m <= 32 * ou.EPS and rr <= 4 * ou.EPS
 
 
+@pytest.mark.gpu
+def test_cpp_batch_object_drives_every_gpu(pkg, ref, tmp_path):
+    """r8b::CDSPResamplerBatch(Device = -1) shards its channels over the visible GPUs behind the C-ABI; on a one-GPU box
+    R8BGPU_FORCE_SHARDS exercises the same front."""
+    exe = build_demo(pkg)
+    n_ch, frames, block = 5, 20000, 4096
+    x = ou.white_noise(n_ch, frames, 17)
+    fin, fout = str(tmp_path / "in.f64"), str(tmp_path / "out.f64")
+    x.tofile(fin)
+    env = dict(os.environ)
+    if pkg.device_count() < 2:
+        env["R8BGPU_FORCE_SHARDS"] = "2"
+    res = subprocess.run([exe, fin, fout, str(n_ch), str(frames), "44100", "96000", str(block), "--batch"], check=True,
+                         capture_output=True, text=True, env=env)
+    assert int(res.stdout) == max(2, min(pkg.device_count(), n_ch))
+    raw = open(fout, "rb").read()
+    pos = 0
+    for c in range(n_ch):
+        n = int(np.frombuffer(raw[pos:pos + 8], dtype=np.int64)[0])
+        y = np.frombuffer(raw[pos + 8:pos + 8 + 8 * n], dtype=np.float64)
+        pos += 8 + 8 * n
+        r = ref.Resampler(44100.0, 96000.0, block, 2.0, 180.15)
+        yr = np.concatenate([r.process(x[c, i:i + block]) for i in range(0, frames, block)])
+        assert len(yr) == n
+        m, rr = ou.parity_metrics(y, yr)
+        assert m <= 32 * ou.EPS and rr <= 4 * ou.EPS
+
+
 # ---- the reference's DLL interface (DLL/r8bsrc.h): libr8bsrc.so driven from plain C -------------------------------------
 DLL_EXE = os.path.join(ROOT, "tests", "cpp", "dll_demo")
 
