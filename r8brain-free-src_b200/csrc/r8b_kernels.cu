@@ -569,6 +569,10 @@ void launch_save_tail(const double* cur, long long cur_stride, long long cur_bas
 #endif
 constexpr int HB_NT = R8BGPU_HB_NT;
 __device__ __forceinline__ int hb_pad(int i) { return i + (i >> 2); }
+// Layout of one shared-memory stream buffer: element i at i + (i >> sh).  sh = 2 (hb_pad) suits hb_stage, whose lanes read
+// 4 samples apart; the buffer the fused last-two-stages pass reads -- lanes 2 samples apart -- uses sh = 4: with hb_pad its
+// loads and the producing stage's stores were both 2-way bank-conflicted (ncu: 4.05 wavefronts per LDS.64 instead of 2).
+__device__ __forceinline__ int hb_lay(int i, int sh) { return i + (i >> sh); }
 
 // One cascade stage for a CTA: every thread produces 4 consecutive input positions (8 outputs) from a
 // register window of 2T+3 samples -- 2T+3 shared-memory loads instead of 4*2T.  All indices are 32-bit
@@ -577,7 +581,7 @@ __device__ __forceinline__ int hb_pad(int i) { return i + (i >> 2); }
 // 5q (loads) / 10q (stores) plus a warp-uniform term.
 template <int T>
 __device__ __forceinline__ void hb_stage(const double* __restrict__ in, long long in_lo, const double* __restrict__ f,
-                                         long long L, long long H, double* __restrict__ out, bool last,
+                                         long long L, long long H, double* __restrict__ out, bool last, int osh,
                                          const HbCascadeParams& p, const DstView& dst, int ch, int tid)
 {
     const long long n_lo = (L >= 0) ? L / 2 : -((-L + 1) / 2);               // floor(L/2)
@@ -634,14 +638,11 @@ __device__ __forceinline__ void hb_stage(const double* __restrict__ in, long lon
             }
         } else if (!neg && j0 >= 0 && j0 + 8 <= NL) {
 #pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int o = cj + m;
-                out[10 * q + o + (o >> 2)] = v[m];
-            }
+            for (int m = 0; m < 8; m++) out[hb_lay(j0 + m, osh)] = v[m];
         } else {
 #pragma unroll
             for (int m = 0; m < 8; m++)
-                if (j0 + m >= 0 && j0 + m < NL) out[hb_pad(j0 + m)] = (L + j0 + m < 0) ? 0.0 : v[m];
+                if (j0 + m >= 0 && j0 + m < NL) out[hb_lay(j0 + m, osh)] = (L + j0 + m < 0) ? 0.0 : v[m];
         }
     }
 }
@@ -650,7 +651,7 @@ __device__ __forceinline__ void hb_stage(const double* __restrict__ in, long lon
 // global memory; s_{c-1} exists only in registers.  L, H: the tile's range of s_c (L >= 0, multiple of 8 apart).
 template <int T1, int T2>
 __device__ __forceinline__ void hb_stage_last2(const double* __restrict__ in, long long in_lo, const double* __restrict__ f1,
-                                               const double* __restrict__ f2, long long L, long long H,
+                                               const double* __restrict__ f2, long long L, long long H, int ish,
                                                const HbCascadeParams& p, const DstView& dst, int ch, int tid)
 {
     using G = HbFuseGeom<T1, T2>;
@@ -673,7 +674,7 @@ __device__ __forceinline__ void hb_stage_last2(const double* __restrict__ in, lo
     for (int q = tid; q < n_items; q += HB_NT) {
         const int o0 = base + 2 * q;
         double y8[8];
-        hb_fused_item<T1, T2>(fr, gr, [&](int s) { return in[hb_pad(o0 + s)]; }, n_lo + 4LL * q, neg, y8);
+        hb_fused_item<T1, T2>(fr, gr, [&](int s) { return in[hb_lay(o0 + s, ish)]; }, n_lo + 4LL * q, neg, y8);
         const int j0 = 8 * q;
         if (vec256 && j0 >= jl && j0 + 8 <= jh) {
             store8_256(obase + j0, y8);
@@ -698,14 +699,14 @@ bool hb_last2_supported(int t1, int t2) { return t1 >= 1 && t1 <= 6 && t2 >= 1 &
 
 template <int T1>
 __device__ __forceinline__ void hb_last2_dispatch(int t2, const double* in, long long in_lo, const double* f1, const double* f2,
-                                                  long long L, long long H, const HbCascadeParams& p, const DstView& dst,
+                                                  long long L, long long H, int ish, const HbCascadeParams& p, const DstView& dst,
                                                   int ch, int tid)
 {
     switch (t2) {
-    case 1: hb_stage_last2<T1, 1>(in, in_lo, f1, f2, L, H, p, dst, ch, tid); break;
-    case 2: hb_stage_last2<T1, 2>(in, in_lo, f1, f2, L, H, p, dst, ch, tid); break;
-    case 3: hb_stage_last2<T1, 3>(in, in_lo, f1, f2, L, H, p, dst, ch, tid); break;
-    default: hb_stage_last2<T1, 4>(in, in_lo, f1, f2, L, H, p, dst, ch, tid); break;
+    case 1: hb_stage_last2<T1, 1>(in, in_lo, f1, f2, L, H, ish, p, dst, ch, tid); break;
+    case 2: hb_stage_last2<T1, 2>(in, in_lo, f1, f2, L, H, ish, p, dst, ch, tid); break;
+    case 3: hb_stage_last2<T1, 3>(in, in_lo, f1, f2, L, H, ish, p, dst, ch, tid); break;
+    default: hb_stage_last2<T1, 4>(in, in_lo, f1, f2, L, H, ish, p, dst, ch, tid); break;
     }
 }
 
@@ -722,12 +723,14 @@ __global__ void __launch_bounds__(HB_NT, R8BGPU_HB_MINB) k_hbup_cascade(HbCascad
     const int ch = blockIdx.y;
     const long long A = p.a0 + (long long) blockIdx.x * p.w; // tile = s0 positions [A, A + w)
     const int c = p.n_stages;
+    // layout shift of stream buffer k: the one the fused last-two-stages pass reads is laid out for its 2-sample lane stride
+    auto sh_of = [&](int k) { return (p.fuse_last2 && k == c - 2) ? 4 : 2; };
 
     // stage 0: gather the input segment
     {
         const long long lo = A - p.lo_off[0], hi = A + p.w + p.hi_off[0];
         double* b0 = hsm + p.boff[0];
-        for (long long n = lo + tid; n < hi; n += HB_NT) b0[hb_pad((int) (n - lo))] = (n < 0) ? 0.0 : src_read(src, ch, n);
+        for (long long n = lo + tid; n < hi; n += HB_NT) b0[hb_lay((int) (n - lo), sh_of(0))] = (n < 0) ? 0.0 : src_read(src, ch, n);
     }
     __syncthreads();
 #pragma unroll 1
@@ -739,12 +742,12 @@ __global__ void __launch_bounds__(HB_NT, R8BGPU_HB_MINB) k_hbup_cascade(HbCascad
             const double* f1 = p.taps[k];
             const double* f2 = p.taps[k + 1];
             switch (p.ntaps[k]) {
-            case 1: hb_last2_dispatch<1>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
-            case 2: hb_last2_dispatch<2>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
-            case 3: hb_last2_dispatch<3>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
-            case 4: hb_last2_dispatch<4>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
-            case 5: hb_last2_dispatch<5>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
-            default: hb_last2_dispatch<6>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, p, dst, ch, tid); break;
+            case 1: hb_last2_dispatch<1>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, sh_of(k), p, dst, ch, tid); break;
+            case 2: hb_last2_dispatch<2>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, sh_of(k), p, dst, ch, tid); break;
+            case 3: hb_last2_dispatch<3>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, sh_of(k), p, dst, ch, tid); break;
+            case 4: hb_last2_dispatch<4>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, sh_of(k), p, dst, ch, tid); break;
+            case 5: hb_last2_dispatch<5>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, sh_of(k), p, dst, ch, tid); break;
+            default: hb_last2_dispatch<6>(p.ntaps[k + 1], in, in_lo, f1, f2, L2, H2, sh_of(k), p, dst, ch, tid); break;
             }
             break;
         }
@@ -754,20 +757,20 @@ __global__ void __launch_bounds__(HB_NT, R8BGPU_HB_MINB) k_hbup_cascade(HbCascad
         double* out = last ? nullptr : hsm + p.boff[k + 1];
         const double* __restrict__ f = p.taps[k];
         switch (p.ntaps[k]) {
-        case 1: hb_stage<1>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 2: hb_stage<2>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 3: hb_stage<3>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 4: hb_stage<4>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 5: hb_stage<5>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 6: hb_stage<6>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 7: hb_stage<7>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 8: hb_stage<8>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 9: hb_stage<9>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 10: hb_stage<10>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 11: hb_stage<11>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 12: hb_stage<12>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        case 13: hb_stage<13>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
-        default: hb_stage<14>(in, in_lo, f, L, H, out, last, p, dst, ch, tid); break;
+        case 1: hb_stage<1>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 2: hb_stage<2>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 3: hb_stage<3>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 4: hb_stage<4>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 5: hb_stage<5>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 6: hb_stage<6>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 7: hb_stage<7>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 8: hb_stage<8>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 9: hb_stage<9>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 10: hb_stage<10>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 11: hb_stage<11>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 12: hb_stage<12>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        case 13: hb_stage<13>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
+        default: hb_stage<14>(in, in_lo, f, L, H, out, last, sh_of(k + 1), p, dst, ch, tid); break;
         }
         __syncthreads();
     }
