@@ -1103,6 +1103,7 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.stage_off = (p.ir == 8 && !(p.flags & 4) && fused2_smem_bytes(p.gbank_smem_len, true) <= kFused2SmemMax &&
                                !getenv("R8BGPU_NO_STAGE")) ? fused2_stage_off(p.gbank_smem_len) : 0;
                 p.glog = fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
+                p.mbu = fused2_choose_mbu(p.span, f.in_step, f.out_step);
                 launch_up2_frac2(p, src, dst, b->n_sm, st);
             } else {
                 p.c_tab = d.c_tab_v1;

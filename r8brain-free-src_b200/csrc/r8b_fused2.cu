@@ -20,6 +20,7 @@
 #include "r8b_kernels.h"
 
 #include <cstdint>
+#include <type_traits>
 
 #include "r8b_fused2_core.cuh"
 
@@ -302,51 +303,59 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
                 mt.load(si);
                 const int n_mu = mt.n_j > 0 ? mma_units(p, mt.c_cnt) : 0, ksteps = p.smaxp >> 2;
                 double* const so = s_o[h];
-                // NQ units in flight per warp (different phase groups)
+                // NQ units in flight per warp (different phase groups); MB = blocks per unit, a per-call choice (p.mbu)
                 constexpr int NQ = R8B_F2_PAIR ? 2 : 1, WS = HT / 32;
-                MmaUnit mu[NQ];
+                auto run_units = [&](auto mb_tag) {
+                    constexpr int MB = decltype(mb_tag)::value;
+                    MmaUnit mu[NQ];
 #pragma unroll
-                for (int q = 0; q < NQ; q++) mu[q].set(wh + q * WS, n_groups);
-                for (int unit = wh; unit < n_mu; unit += NQ * WS) {
-                    int yo[NQ][MBU];
-                    const double* gb[NQ];
-                    double acc[NQ][MBU][2];
-#pragma unroll
-                    for (int q = 0; q < NQ; q++) {
-                        const int goff = s_goff[mu[q].g];
-#pragma unroll
-                        for (int i = 0; i < MBU; i++) {
-                            yo[q][i] = mma_a_index(p, mt, mu[q], goff, i, lane);
-                            acc[q][i][0] = acc[q][i][1] = 0.0;
-                        }
-                        gb[q] = sbank + mma_b_index(p, mu[q], lane);
-                    }
-                    auto kstep = [&](int ks) {
+                    for (int q = 0; q < NQ; q++) mu[q].set(wh + q * WS, n_groups);
+                    for (int unit = wh; unit < n_mu; unit += NQ * WS) {
+                        int yo[NQ][MB];
+                        const double* gb[NQ];
+                        double acc[NQ][MB][2];
 #pragma unroll
                         for (int q = 0; q < NQ; q++) {
-                            const double bq = gb[q][ks * 32];
+                            const int goff = s_goff[mu[q].g];
 #pragma unroll
-                            for (int i = 0; i < MBU; i++) {
-                                const int yi = yo[q][i] + 4 * ks;
-                                dmma884(acc[q][i][0], acc[q][i][1], PADV ? yb[ylay(yi, p.ysh)] : yb[yi], bq);
+                            for (int i = 0; i < MB; i++) {
+                                yo[q][i] = mma_a_index(p, mt, mu[q], goff, i, lane);
+                                acc[q][i][0] = acc[q][i][1] = 0.0;
                             }
+                            gb[q] = sbank + mma_b_index(p, mu[q], lane);
                         }
-                    };
-                    if (R8B_F2_KUNROLL && ksteps == 8) { // 24..28-tap banks padded to 32: the common case, fully unrolled
+                        auto kstep = [&](int ks) {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ks++) kstep(ks);
-                    } else {
+                            for (int q = 0; q < NQ; q++) {
+                                const double bq = gb[q][ks * 32];
+#pragma unroll
+                                for (int i = 0; i < MB; i++) {
+                                    const int yi = yo[q][i] + 4 * ks;
+                                    dmma884(acc[q][i][0], acc[q][i][1], PADV ? yb[ylay(yi, p.ysh)] : yb[yi], bq);
+                                }
+                            }
+                        };
+                        if (R8B_F2_KUNROLL && ksteps == 8) { // 24..28-tap banks padded to 32: the common case, fully unrolled
+#pragma unroll
+                            for (int ks = 0; ks < 8; ks++) kstep(ks);
+                        } else {
 #pragma unroll 4
-                        for (int ks = 0; ks < ksteps; ks++) kstep(ks);
-                    }
-#pragma unroll
-                    for (int q = 0; q < NQ; q++) {
-                        if (unit + q * WS < n_mu) {
-#pragma unroll
-                            for (int i = 0; i < MBU; i++) mma_store(p, dst, t.ch, mt, so, mu[q], i, lane, acc[q][i][0], acc[q][i][1]);
+                            for (int ks = 0; ks < ksteps; ks++) kstep(ks);
                         }
-                        mu[q].advance(NQ * WS, n_groups);
+#pragma unroll
+                        for (int q = 0; q < NQ; q++) {
+                            if (unit + q * WS < n_mu) {
+#pragma unroll
+                                for (int i = 0; i < MB; i++) mma_store(p, dst, t.ch, mt, so, mu[q], i, lane, acc[q][i][0], acc[q][i][1]);
+                            }
+                            mu[q].advance(NQ * WS, n_groups);
+                        }
                     }
+                };
+                switch (mma_mbu(p)) {
+                case 2: run_units(std::integral_constant<int, 2>()); break;
+                case 4: run_units(std::integral_constant<int, 4>()); break;
+                default: run_units(std::integral_constant<int, 3>()); break;
                 }
             } else if (si[0] > 0) {
                 const int n_tasks = TaskGeom<IRV, GLOG>::n_tasks(p, si[1]);

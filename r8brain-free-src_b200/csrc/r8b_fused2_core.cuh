@@ -483,7 +483,7 @@ R8B_HD void interp_store_direct(const FusedParams& p, const DstView& dst, int ch
 // with two CONSECUTIVE outputs of one stepping cycle and four lanes hold one 64-byte output row, so results go
 // straight from the accumulators to global memory with no transposition.  Against the register-tiled FMA loop the
 // shared-memory traffic per multiply-add halves (each loaded Y value feeds 8 products, each Bp value MBU*8) and
-// 256 multiply-adds issue as one instruction.  A work unit = one group x MBU blocks of 8 stepping cycles.
+// 256 multiply-adds issue as one instruction.  A work unit = one group x mbu (2..4) blocks of 8 stepping cycles.
 //
 // Which stepping cycle a fragment row stands for is free.  An LDS.64 is served one half-warp at a time, and the
 // four rows of a half-warp (4 consecutive doubles each) are conflict-free exactly when their starts are 4 or 12
@@ -491,14 +491,16 @@ R8B_HD void interp_store_direct(const FusedParams& p, const DstView& dst, int ch
 // kappa = 4 gives 4*in_step = 4 or 12 (mod 16): so the rows of a half-warp take cycles 4 apart, and two blocks
 // interleave to cover 16 consecutive cycles:  cycle(block, row) = 16*(block/2) + 4*(row%4) + 2*(block%2) + row/4.
 // (Even in_step: the padded y layout makes the stride odd on average; the same map is used.)
-constexpr int MBU = 3;
+constexpr int MBU_MAX = 4; // blocks per work unit: 2, 3 or 4, chosen per call (FusedParams::mbu; fused2_choose_mbu())
+R8B_HD int mma_mbu(const FusedParams& p) { return p.mbu >= 2 && p.mbu <= MBU_MAX ? p.mbu : 3; }
 
 R8B_HD int mma_cycle(int block, int row) { return 16 * (block >> 1) + 4 * (row & 3) + 2 * (block & 1) + (row >> 2); }
 
 R8B_HD int mma_units(const FusedParams& p, int c_cnt)
 {
     const int n_groups = (p.out_step + 7) / 8, n_mb = 2 * (c_cnt / 16 + 1);
-    return n_groups * ((n_mb + MBU - 1) / MBU);
+    const int mbu = mma_mbu(p);
+    return n_groups * ((n_mb + mbu - 1) / mbu);
 }
 
 // A work unit's place in the tile: its phase group and which MBU blocks of cycles it covers.  Units are dealt to the
@@ -537,7 +539,7 @@ struct MmaTile {
 // y index (before the padded-layout map) of the lane's A element of block i at K-step 0
 R8B_HD int mma_a_index(const FusedParams& p, const MmaTile& mt, const MmaUnit& u, int goff, int i, int lane)
 {
-    int c = mma_cycle(u.chunk * MBU + i, lane >> 2);
+    int c = mma_cycle(u.chunk * mma_mbu(p) + i, lane >> 2);
     if (c > mt.c_cnt) c = mt.c_cnt;          // rows past the last cycle compute something valid and never store
     int li = c * p.in_step + goff + mt.wbase;
     if (li < 0) li = 0;
@@ -553,7 +555,7 @@ R8B_HD int mma_b_index(const FusedParams& p, const MmaUnit& u, int lane) { retur
 R8B_HD void mma_store(const FusedParams& p, const DstView& dst, int ch, const MmaTile& mt, double* s_o, const MmaUnit& u, int i, int lane,
                       double c0, double c1)
 {
-    const int c = mma_cycle(u.chunk * MBU + i, lane >> 2);
+    const int c = mma_cycle(u.chunk * mma_mbu(p) + i, lane >> 2);
     if (c > mt.c_cnt) return;
     const int rr = p.delta + u.g * 8 + 2 * (lane & 3);
     const int j = c * p.out_step + rr + mt.jshift;

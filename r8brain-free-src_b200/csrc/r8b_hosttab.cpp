@@ -290,4 +290,21 @@ int fused2_choose_glog(int span, int in_step, int out_step, int ir)
     return best > 2 ? 2 : best;
 }
 
+int fused2_choose_mbu(int span, int in_step, int out_step)
+{
+    // a tile owns ~span / in_step + 1 stepping cycles, handled in pairs of 8-cycle blocks (16 consecutive cycles)
+    const int cycles = span / in_step + 2, n_mb = 2 * ((cycles - 1) / 16 + 1), n_groups = (out_step + 7) / 8;
+    int best = 3, best_cost = INT_MAX;
+    for (int mbu = 2; mbu <= 4; mbu++) {
+        const int units = n_groups * ((n_mb + mbu - 1) / mbu);
+        const int cost = ((units + 7) / 8) * mbu;
+        if (cost < best_cost || (cost == best_cost && mbu == 3)) {
+            best_cost = cost;
+            best = mbu;
+        }
+    }
+    if (const char* e = getenv("R8BGPU_F2_MBU")) best = atoi(e);
+    return best < 2 ? 2 : (best > 4 ? 4 : best);
+}
+
 } // namespace r8bgpu

@@ -59,5 +59,7 @@ void fused_whole_fields(FusedParams& p, const StageDesc& frac, long long e0, lon
 // 16-byte boundaries of the block (bulk-copied input tiles); -1: no constraint.
 void fused2_tiles(FusedParams& p, const FusedGeom& g, int cur_parity);
 int fused2_choose_glog(int span, int in_step, int out_step, int ir);
+// blocks of 8 stepping cycles per work unit of the tensor-path interpolation: fewest (rounds over a half's 8 warps) x blocks
+int fused2_choose_mbu(int span, int in_step, int out_step);
 
 } // namespace r8bgpu

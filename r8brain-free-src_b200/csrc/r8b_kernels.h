@@ -182,6 +182,7 @@ struct FusedParams {
     int glog;                // log2 of the phase groups a warp covers per instruction (lanes = 32>>glog cycles x 1<<glog groups)
     int flags;               // bit 0: ping-pong token around the interpolation, bit 1: bulk-copy input tiles
     const double2* tw_tab;   // 512 entries: tw2t[q*16+r] = W_256^(r q), then tw1t[q*16+r] = W_M^(r q)
+    int mbu;                 // tensor-path interpolation: blocks of 8 stepping cycles per work unit (2..4; 0 = 3)
     int up;                  // BlockConvolver up-factor of the fused pair: 2 (default, also when 0) or 1
     int ylen;                // doubles of the tile's stream between the two stages held in shared memory (2*FM for up 2, FM for up 1)
     const double2* cd_tab;   // up == 2, phase C fused into the first inverse pass: [q3 < 16][g < 256] spectrum at slot 16 g + q3,

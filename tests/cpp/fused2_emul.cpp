@@ -45,7 +45,8 @@ void interp_tc(const FusedParams& p, const DstView& dst, const Tile& t, const do
         MmaUnit mu;
         mu.set(w, n_groups);
         for (int unit = w; unit < n_mu; unit += HT / 32, mu.advance(HT / 32, n_groups)) {
-            double acc[MBU][32][2] = {};
+            const int MBU = mma_mbu(p);
+            double acc[MBU_MAX][32][2] = {};
             for (int ks = 0; ks < ksteps; ks++) {
                 double b[32];
                 for (int lane = 0; lane < 32; lane++) b[lane] = sbank[mma_b_index(p, mu, lane) + ks * 32];
@@ -258,6 +259,7 @@ int f2emul_process(void* h, const double* x, int l, double* out, int out_cap)
         p.ir = E.B.ir;
         p.gbank_smem_len = E.B.n_groups * E.B.smaxp * E.B.ir;
         p.n_ch = 1;
+        p.mbu = fused2_choose_mbu(p.span, f.in_step, f.out_step);
         p.glog = E.tc ? 0 : E.glog_force >= 0 ? E.glog_force : fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
         SrcView src;
         src.ring = E.ring.data();
