@@ -125,6 +125,7 @@ struct StageDev {
     double2* c_tab_v1 = nullptr; // round-1 fused kernel: its two spectrum values per frequency pair in thread order
     bool bank_frag_order = false; // grouped bank stored in mma fragment order (only the tensor-path interpolation reads it)
     bool f2_ok = false;
+    bool f2_poly = false; // order-2 interpolator on the v2 kernel's tensor path (decided per call: near-integer ratios)
     bool f2_copy = false; // BlockConvolver 2/1 alone on the v2 kernel (phase E copies the 2x stream out)
     FusedGeom fgeom;
 };
@@ -472,6 +473,10 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                     fg.ok = false;
             }
             if (fg.ok) {
+                // (opt-in: measured slower than the round-1 kernel's staged-row path)
+                if (st[i + 1].kind == ST_FRAC_POLY && fg.up == 2 && (b->f2_flags & 4) && !getenv("R8BGPU_FUSED_V1") && getenv("R8BGPU_POLY_V2") &&
+                    (st[i + 1].bank.filter_len & 1) == 0 && st[i + 1].bank.filter_len <= 32)
+                    d.f2_poly = true;
                 d.fused_with_next = true;
                 b->dev[i + 1].fused_into_prev = true;
                 d.fgeom = fg;
@@ -775,7 +780,7 @@ int r8bgpu_batch_stage_kernel(const r8bgpu_batch* b, int stage, char* name, int 
         nm = "(fused)";
         span = 0;
     } else if (d.fused_with_next) {
-        nm = d.f2_ok ? "k_up2_frac2" : "k_up2_frac";
+        nm = d.f2_ok ? "k_up2_frac2" : d.f2_poly ? "k_up2_frac2<poly>|k_up2_frac" : "k_up2_frac";
         span = 2;
     } else if (d.down_casc_len >= 2) {
         nm = "k_hbdown_cascade";
@@ -1015,7 +1020,15 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 p.in_step = f.in_step;
                 p.out_step = f.out_step;
             }
-            const bool v2 = d.f2_ok && p.mode == 0;
+            // order-2 bank on the v2 kernel: ratios within 1e-3 of an integer 1..3 (windows of consecutive outputs N apart)
+            bool v2_poly = false;
+            if (p.mode == 1 && d.f2_poly) {
+                const double ratio = f.src_rate / f.dst_rate;
+                const long long nn = llround(ratio);
+                v2_poly = nn >= 1 && nn <= 3 && fabs(ratio - (double) nn) < 1e-3 * (double) nn;
+                if (v2_poly) p.poly_n = (int) nn;
+            }
+            const bool v2 = (d.f2_ok && p.mode == 0) || v2_poly;
             if (v2) {
                 fused2_tiles(p, d.fgeom, i == 0 ? (int) (c.n0 & 1) : -1);
             } else {
@@ -1057,7 +1070,8 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
             p.p0 = fc.p0;
             p.pos_dp = fd.ft_dp;
             p.pos_fpos = fd.ft_fpos;
-            if (p.mode == 1 && (p.flen & 1) == 0 && !getenv("R8BGPU_BANK_GLOBAL")) {
+            p.bank = fd.bank;
+            if (p.mode == 1 && !v2_poly && (p.flen & 1) == 0 && !getenv("R8BGPU_BANK_GLOBAL")) {
                 // bank-row drift per output, in rows: frac(ssr/dsr) * fracs upward, or (1 - frac) * fracs downward
                 const double ratio = p.ssr / p.dsr, fr = ratio - floor(ratio);
                 const double outs = 2.0 * p.span / ratio + 4.0; // outputs one tile pair can own
@@ -1102,8 +1116,13 @@ static void launch_call(r8bgpu_batch* b, const double* d_in, size_t in_stride, i
                 if (!fd.bank_frag_order) p.flags &= ~4; // (the bank layout decides: see batch_create)
                 p.stage_off = (p.ir == 8 && !(p.flags & 4) && fused2_smem_bytes(p.gbank_smem_len, true) <= kFused2SmemMax &&
                                !getenv("R8BGPU_NO_STAGE")) ? fused2_stage_off(p.gbank_smem_len) : 0;
-                p.glog = fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
-                p.mbu = fused2_choose_mbu(p.span, f.in_step, f.out_step);
+                if (v2_poly) { // plain y layout; no grouped bank, no staging area in shared memory
+                    p.ysh = 31;
+                    p.gbank_smem_len = 0;
+                    p.stage_off = 0;
+                }
+                p.glog = v2_poly ? 0 : fused2_choose_glog(p.span, f.in_step, f.out_step, p.ir);
+                p.mbu = v2_poly ? 3 : fused2_choose_mbu(p.span, f.in_step, f.out_step);
                 launch_up2_frac2(p, src, dst, b->n_sm, st);
             } else {
                 p.c_tab = d.c_tab_v1;

@@ -23,6 +23,7 @@
 #include <type_traits>
 
 #include "r8b_fused2_core.cuh"
+#include "r8b_poly.cuh"
 
 // experiment knobs of the tensor-path interpolation loop: units in flight per warp, unrolled K loop
 #ifndef R8B_F2_PAIR
@@ -145,7 +146,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // mirroring the real-input forward transform, 4096 samples per tile -- TC only)
 // COPY: no interpolator follows -- phase E writes the tile's owned positions of the 2x-rate stream to the destination
 // (the BlockConvolver 2/1 alone: chains that continue with half-band upsamplers, or end there); no bank is loaded.
-template <int IRV, bool PADV, int GLOG, bool TC, int UP = 2, bool COPY = false>
+// POLY: the interpolator is the order-2 bank (CDSPFracInterpolator::convolve2, CDSPFracInterpolator.h:1069-1179) of a
+// ratio close to an integer N: eight consecutive outputs whose windows start N samples apart and whose bank rows are two
+// neighbours {r, r+1} form a GEMM  D[j][n] = sum_i y[p_j + i] * B[i][n]  with B's columns = (c0, c1, c2) of the two rows;
+// output j = D[j][c0] + x_j D[j][c1] + x_j^2 D[j][c2] of its own row.  Blocks that do not fit (a position slip, the row
+// index wrapping) are computed one output per quad from the bank in global memory.
+template <int IRV, bool PADV, int GLOG, bool TC, int UP = 2, bool COPY = false, bool POLY = false>
 __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ FusedParams p, const __grid_constant__ SrcView src,
                                                       const __grid_constant__ DstView dst)
 {
@@ -169,11 +175,11 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
         for (int i = 0; i < 5; i++) mbar_init(&mb[i], 1);
         fence_mbar_init();
     }
-    if (!COPY && tid < n_groups) s_goff[tid] = __ldg(&p.goff[p.delta + tid * IRV]);
+    if (!COPY && !POLY && tid < n_groups) s_goff[tid] = __ldg(&p.goff[p.delta + tid * IRV]);
     __syncthreads();
     if (tid == 0) {
         // tables: one transaction barrier, 1 + n_groups bulk copies
-        const int n_bank = COPY ? 0 : n_groups;
+        const int n_bank = (COPY || POLY) ? 0 : n_groups;
         mbar_expect_tx(&mb[0], (uint32_t) (512 * sizeof(double2) + (size_t) n_bank * esz * sizeof(double)));
         bulk_g2s(tw2, p.tw_tab, 512 * sizeof(double2), &mb[0]);
         for (int g = 0; g < n_bank; g++)
@@ -223,7 +229,12 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
             }
             fwd_pass1_r8(v, buf, tw2, twf, ht);
         }
-        if (!COPY && ht == HT - 1) interp_prepare(p, dst, t, s_i[h], &s_o[h]);
+        if (POLY && ht == HT - 1) { // the tile's outputs [ka, kb) of this call: positions in [A0, A1)
+            const long long nk = p.e1 - p.e0;
+            s_i[h][0] = (int) poly_first_k(p, t.A0, nk);
+            s_i[h][1] = (int) poly_first_k(p, t.A1, nk);
+        }
+        if (!COPY && !POLY && ht == HT - 1) interp_prepare(p, dst, t, s_i[h], &s_o[h]);
         bar_half(h);
         // B. the two radix-16 passes act on 256-point blocks owned by one half-warp each
         constexpr bool fuse_c = (UP == 2); // the 1x pair keeps its separate split pass
@@ -284,7 +295,116 @@ __global__ void __launch_bounds__(NT2, 1) k_up2_frac2(const __grid_constant__ Fu
         {
             const double* yb = reinterpret_cast<const double*>(buf);
             const int* si = s_i[h];
-            if constexpr (COPY) {
+            if constexpr (POLY) {
+                // A warp takes 32 consecutive outputs per round: every lane evaluates ONE position (the timing expression costs a
+                // double division), the four blocks of 8 read their rows' values by shuffle.  When all four blocks sit on the
+                // same pair of bank rows -- 32 outputs drift ~1.15 rows, so mostly -- their DMMA chains are interleaved (four
+                // independent accumulators hide the dependent-issue latency); otherwise block by block.
+                const int ka = si[0], kb = si[1], N = p.poly_n, flen = p.flen, ksteps = (flen + 3) >> 2;
+                const int row = lane >> 2, kq = lane & 3;
+                const unsigned full = 0xffffffffu;
+                const int n_rounds = (kb - ka + 31) >> 5;
+                int cached_row = -2;
+                double bq[8]; // B fragment of every K-step for the cached row pair (flen <= 32)
+                auto load_b = [&](int fmin) { // column n = lane/4: component n>>1 of row fmin + (n&1); columns 6, 7 unused
+                    cached_row = fmin;
+                    int brow = fmin + (row & 1);
+                    if (brow > p.fracs) brow = p.fracs;
+                    const double* __restrict__ br = p.bank + (long long) brow * 3 * flen + (row >> 1);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ks++) {
+                        const int tap = 4 * ks + kq;
+                        bq[ks] = (ks < ksteps && tap < flen && row < 6) ? __ldg(br + 3 * tap) : 0.0;
+                    }
+                };
+                for (int rd = wh; rd < n_rounds; rd += HT / 32) {
+                    const int k_own = ka + 32 * rd + lane;
+                    const bool v_own = k_own < kb;
+                    long long ip;
+                    double fpos;
+                    poly_position(p, v_own ? k_own : kb - 1, ip, fpos);
+                    double x_own = __dmul_rn(fpos, (double) p.fracs);
+                    const int f_own = __double2int_rz(x_own);
+                    x_own = __dsub_rn(x_own, (double) f_own);
+                    const int y_own = (int) (ip - p.fll - 2 * t.w);
+                    int fm = v_own ? f_own : 0x7fffffff; // min row of the lane's block of 8 outputs
+                    fm = min(fm, __shfl_xor_sync(full, fm, 1));
+                    fm = min(fm, __shfl_xor_sync(full, fm, 2));
+                    fm = min(fm, __shfl_xor_sync(full, fm, 4));
+                    // per block q: this lane's row (lane 8q + row of the round)
+                    int yi[4], fr[4], ya0[4], fmin[4];
+                    bool vr[4], fast[4];
+                    bool all_fast = true;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int srcl = 8 * q + row;
+                        yi[q] = __shfl_sync(full, y_own, srcl);
+                        fr[q] = __shfl_sync(full, f_own, srcl);
+                        vr[q] = __shfl_sync(full, (int) v_own, srcl) != 0;
+                        ya0[q] = __shfl_sync(full, y_own, 8 * q);
+                        fmin[q] = __shfl_sync(full, fm, 8 * q);
+                        const bool blk_live = __shfl_sync(full, (int) v_own, 8 * q) != 0; // block has at least one output
+                        const bool fits = !vr[q] || (yi[q] == ya0[q] + N * row && fr[q] - fmin[q] <= 1);
+                        fast[q] = blk_live && __all_sync(full, fits) && ya0[q] >= 0 && ya0[q] + 7 * N + 4 * ksteps <= p.ylen;
+                        all_fast = all_fast && (fast[q] || !blk_live);
+                    }
+                    // do the live blocks share block 0's row pair?
+                    bool same = all_fast;
+#pragma unroll
+                    for (int q = 1; q < 4; q++) {
+                        const bool blk_live = __shfl_sync(full, (int) v_own, 8 * q) != 0;
+                        if (blk_live) {
+                            const bool in_pair = !vr[q] || (fr[q] - fmin[0] >= 0 && fr[q] - fmin[0] <= 1);
+                            same = same && __all_sync(full, in_pair);
+                        }
+                    }
+                    double res[4] = {0.0, 0.0, 0.0, 0.0}; // output of (block q, this lane's row), meaningful in lanes kq == 0
+                    if (same) {
+                        if (fmin[0] != cached_row) load_b(fmin[0]);
+                        double c0[4] = {0.0, 0.0, 0.0, 0.0}, c1[4] = {0.0, 0.0, 0.0, 0.0};
+                        const double* ya[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) ya[q] = yb + (fast[q] ? ya0[q] : 0) + N * row + kq;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++)
+                            if (ks < ksteps) {
+#pragma unroll
+                                for (int q = 0; q < 4; q++) dmma884(c0[q], c1[q], ya[q][4 * ks], bq[ks]);
+                            }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) res[q] = (fr[q] - fmin[0]) ? c1[q] : c0[q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (!fast[q]) continue; // (warp-uniform)
+                            if (fmin[q] != cached_row) load_b(fmin[q]);
+                            double c0 = 0.0, c1 = 0.0;
+                            const double* yq = yb + ya0[q] + N * row + kq;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ks++)
+                                if (ks < ksteps) dmma884(c0, c1, yq[4 * ks], bq[ks]);
+                            res[q] = (fr[q] - fmin[q]) ? c1 : c0;
+                        }
+                    }
+                    // combine the three components of every row: lanes kq = 0, 1, 2 hold D0, D1, D2
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const double xr = __shfl_sync(full, x_own, 8 * q + row);
+                        const double d1 = __shfl_sync(full, res[q], (lane & ~3) + 1), d2 = __shfl_sync(full, res[q], (lane & ~3) + 2);
+                        double outv = fma(__dmul_rn(xr, xr), d2, fma(xr, d1, res[q]));
+                        const bool slow = vr[q] && !(same || fast[q]);
+                        if (slow && kq == 0 && yi[q] >= 0 && yi[q] + flen <= p.ylen) {
+                            // one output, the reference's own order: c = c0 + c1 x + c2 x^2 per tap, taps ascending
+                            const double x2 = __dmul_rn(xr, xr);
+                            const double* __restrict__ br = p.bank + (long long) fr[q] * 3 * flen;
+                            outv = 0.0;
+                            for (int i = 0; i < flen; i++)
+                                outv = fma(fma(__ldg(br + 3 * i + 2), x2, fma(__ldg(br + 3 * i + 1), xr, __ldg(br + 3 * i))), yb[yi[q] + i], outv);
+                        }
+                        if (vr[q] && kq == 0) dst_write_f(dst, t.ch, p.e0 + ka + 32 * rd + 8 * q + row, outv);
+                    }
+                }
+            } else if constexpr (COPY) {
                 // owned positions [A0, A1) clipped to this call's range; position q sits at y index q - 2 w
                 long long q0 = t.A0 > p.e0 ? t.A0 : p.e0, q1 = t.A1 < p.e1 ? t.A1 : p.e1;
                 const int off = (int) (q0 - 2 * t.w), cnt = q1 > q0 ? (int) (q1 - q0) : 0;
@@ -396,11 +516,11 @@ int fused2_smem_bytes(int bank_doubles, bool staged)
 }
 int fused2_stage_off(int bank_doubles) { return 2 * (2 * FPL2 + 512) + ((bank_doubles + 1) & ~1); }
 
-template <int IRV, bool PADV, int GLOG, bool TC = false, int UP = 2, bool COPY = false>
+template <int IRV, bool PADV, int GLOG, bool TC = false, int UP = 2, bool COPY = false, bool POLY = false>
 static void launch_inst2(const FusedParams& p, const SrcView& src, const DstView& dst, int grid, int smem, cudaStream_t st)
 {
-    ensure_dyn_smem<k_up2_frac2<IRV, PADV, GLOG, TC, UP, COPY>>(227 * 1024);
-    k_up2_frac2<IRV, PADV, GLOG, TC, UP, COPY><<<(unsigned) grid, NT2, smem, st>>>(p, src, dst);
+    ensure_dyn_smem<k_up2_frac2<IRV, PADV, GLOG, TC, UP, COPY, POLY>>(227 * 1024);
+    k_up2_frac2<IRV, PADV, GLOG, TC, UP, COPY, POLY><<<(unsigned) grid, NT2, smem, st>>>(p, src, dst);
 }
 
 // p.n_ch, p.n_tiles, p.span ... describe the call; n_sm = SMs of the device (persistent grid).
@@ -415,6 +535,10 @@ void launch_up2_frac2(const FusedParams& p, const SrcView& src, const DstView& d
 #define R8B_F2_CASE(IRV, GL)                                                              \
     if (pad) launch_inst2<IRV, true, GL>(p, src, dst, grid, smem, st);                    \
     else launch_inst2<IRV, false, GL>(p, src, dst, grid, smem, st);
+    if (p.mode == 1) { // order-2 bank on the tensor path (ratios close to an integer; plain y layout)
+        launch_inst2<8, false, 0, true, 2, false, true>(p, src, dst, grid, smem, st);
+        return;
+    }
     if (p.mode == 2) { // BlockConvolver 2/1 alone
         launch_inst2<8, false, 0, true, 2, true>(p, src, dst, grid, smem, st);
         return;
