@@ -506,7 +506,9 @@ r8bgpu_batch* r8bgpu_batch_create(const r8bgpu_plan* plan, int n_channels, int d
                     cp.ntaps[k] = st[i + k].hb_taps;
                     for (int j = 0; j < st[i + k].hb_taps; j++) cp.taps[k][j] = st[i + k].hb[(size_t) j];
                 }
-                d.down_casc_smem = hbdown_cascade_plan(cp, 100 * 1024 / 8); // two CTAs per SM
+                int hbd_budget = 6400; // doubles per CTA (4 CTAs per SM; measured on 2822400->44100: 3200 0.97, 6400 0.46, 12800 0.53, 25000 0.79 ms)
+                if (const char* e = getenv("R8BGPU_HBD_SMEM_DOUBLES")) hbd_budget = atoi(e);
+                d.down_casc_smem = hbdown_cascade_plan(cp, hbd_budget);
                 if (d.down_casc_smem > 0) {
                     d.down_casc_len = (int) c;
                     for (size_t k = 1; k < c; k++) b->dev[i + k].fused_into_prev = true;
