@@ -530,7 +530,7 @@ int hbdown_cascade_plan(HbDownCascParams& p, int smem_budget_doubles)
 void launch_hbdown_cascade(const HbDownCascParams& p, int smem_bytes, const SrcView& src, const DstView& dst, int n_ch, cudaStream_t st)
 {
     if (p.e1 <= p.e0 || n_ch <= 0 || p.n_tiles <= 0) return;
-    ensure_dyn_smem<k_hbdown_cascade>(smem_bytes > 48 * 1024 ? smem_bytes : 48 * 1024);
+    ensure_dyn_smem<k_hbdown_cascade>(227 * 1024); // opt-in once per device, to the limit: later plans may need more than the first
     k_hbdown_cascade<<<(unsigned) ((long long) p.n_tiles * n_ch), HBDC_NT, smem_bytes, st>>>(p, src, dst);
 }
 
