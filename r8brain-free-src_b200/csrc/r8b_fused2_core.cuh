@@ -116,7 +116,8 @@ R8B_HD void fwd_pass1_r8(double2 (&v)[8], double2* __restrict__ s, const double2
     s[fft_pad(r + 7 * 256)] = cmul<+1>(v[bitrev<8>(7)], cprod(w3, w4));
 }
 
-// C, first half: this thread's four frequency pairs (k, N-k), k <= N/2.  In slot order (k = q1 + 8 q2 + 128 q3,
+// C (up-factor 1; the 2x pair fuses this phase into its first inverse pass, see cd1_*), first half: this thread's four
+// frequency pairs (k, N-k), k <= N/2.  In slot order (k = q1 + 8 q2 + 128 q3,
 // slot = 256 q1 + 16 q2 + q3) those are the slots with q3 < 8; a thread takes runs of 8 consecutive slots.
 R8B_HD int c_freq(int ht, int u) { return freq_of<FN>(16 * ((ht >> 3) + 32 * u) + (ht & 7)); }
 
@@ -130,41 +131,6 @@ R8B_HD void c_load(const double2* __restrict__ buf, int ht, double2 (&z1)[4], do
         z1[u] = buf[fft_pad(s1)];
         z2[u] = buf[fft_pad(s2)];
     }
-}
-
-// C, second half (after every thread has fetched its Z values: the products overwrite them).
-//   A' = Z[k] + conj Z[N-k] = 2 E[k],  B' = -i (Z[k] - conj Z[N-k]) = 2 O[k]
-//   2X[k] = A' + W^k B',  2X[k+N] = A' - W^k B',  X[N-k] = conj X[k+N],  X[M-k] = conj X[k]
-// (the factor 2 lives in G).  k = 0 and k = N/2 pair with themselves; their four stores collapse to two
-// locations written with equal values.
-R8B_HD void c_pair_ops(double2* __restrict__ buf, int k, double2 z1, double2 z2, double2 w, double2 g0, double2 g1, double2 g2,
-                       double2 g3)
-{
-    const double2 a = make_double2(z1.x + z2.x, z1.y - z2.y);
-    const double2 b = make_double2(z1.y + z2.y, z2.x - z1.x);
-    const double2 wb = cmul<+1>(b, w);
-    const double2 x0 = make_double2(a.x + wb.x, a.y + wb.y);
-    const double2 x1 = make_double2(a.x - wb.x, a.y - wb.y);
-    const int s0 = slot_of<FM>(k), s1 = slot_of<FM>(k + FN), s2 = slot_of<FM>(FN - k), s3 = slot_of<FM>((FM - k) & (FM - 1));
-    buf[fft_pad(s0)] = cmul<+1>(x0, g0);
-    buf[fft_pad(s1)] = cmul<+1>(x1, g1);
-    buf[fft_pad(s2)] = cmul<+1>(make_double2(x1.x, -x1.y), g2);
-    buf[fft_pad(s3)] = cmul<+1>(make_double2(x0.x, -x0.y), g3);
-}
-
-// operands from the natural tables (spectrum in slot order, W_M^k): scattered reads, used for the one extra pair k = N/2
-R8B_HD void c_pair(const FusedParams& p, double2* __restrict__ buf, int k, double2 z1, double2 z2)
-{
-    c_pair_ops(buf, k, z1, z2, R8B_LDG(&p.tw[k]), R8B_LDG(&p.spec[slot_of<FM>(k)]), R8B_LDG(&p.spec[slot_of<FM>(k + FN)]),
-               R8B_LDG(&p.spec[slot_of<FM>(FN - k)]), R8B_LDG(&p.spec[slot_of<FM>((FM - k) & (FM - 1))]));
-}
-
-// operands from the thread-ordered table p.c_tab ([u][item][ht]: a warp's 32 loads of one item are 512 contiguous bytes;
-// the natural tables put a warp's 32 operands on 32 different cache lines)
-R8B_HD void c_pair_tab(const FusedParams& p, double2* __restrict__ buf, int ht, int u, double2 z1, double2 z2)
-{
-    const double2* __restrict__ ct = p.c_tab + (u * 5) * HT + ht;
-    c_pair_ops(buf, c_freq(ht, u), z1, z2, R8B_LDG(ct), R8B_LDG(ct + HT), R8B_LDG(ct + 2 * HT), R8B_LDG(ct + 3 * HT), R8B_LDG(ct + 4 * HT));
 }
 
 // ---- phase C fused into the first inverse pass (up-factor 2) -------------------------------------------------------
@@ -278,7 +244,7 @@ R8B_HD void y_store(double2* __restrict__ buf, const double2 (&v)[16], int g, lo
 // The tile's 4096 real outputs come from a 2048-point complex INVERSE transform, the mirror of the real-input forward
 // one:  with Y[k] = X[k] H[k] (k = 0..N, Hermitian beyond),  Z'[k] = (Y[k] + conj Y[N-k]) + i W_M^-k (Y[k] - conj Y[N-k])
 // and IFFT_N(Z')[m] = y[2m] + i y[2m+1].  Per pair (k, N-k), from the forward values z1 = Z[k], z2 = Z[N-k]:
-//   x0 = 2X[k] = a + W^k b,  x1 = 2X[k+N] = a - W^k b   (a, b as in c_pair_ops);   2X[N-k] = conj x1
+//   x0 = 2X[k] = a + W^k b,  x1 = 2X[k+N] = a - W^k b   (a = Z[k] + conj Z[N-k] = 2E[k], b = -i (Z[k] - conj Z[N-k]) = 2O[k]);   2X[N-k] = conj x1
 //   p = x0 h0,  q = conj(x1) h1          (h0 = H[k]/2, h1 = H[N-k]/2; H = FFT(h)/M is real up to rounding)
 //   s = p + conj q,  t = i conj(W^k) (p - conj q);   Z'[k] = s + t,  Z'[N-k] = conj(s - t)
 // k = 0 pairs DC with the Nyquist bin (h1 = H[N]/2) and k = N/2 pairs with itself: both write one slot.

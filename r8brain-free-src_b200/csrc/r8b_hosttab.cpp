@@ -117,18 +117,7 @@ std::vector<double2> build_c_tab(const std::vector<double2>& spec, const std::ve
         ct[(size_t) 12 * HT + 2] = hk(FN / 2);
         return ct;
     }
-    std::vector<double2> ct((size_t) 4 * 5 * HT);
-    for (int u = 0; u < 4; u++)
-        for (int ht = 0; ht < HT; ht++) {
-            const int k = c_freq(ht, u);
-            double2* e = &ct[(size_t) (u * 5) * HT + ht];
-            e[0] = tw[(size_t) k];
-            e[HT] = spec[(size_t) slot_of<FM>(k)];
-            e[2 * HT] = spec[(size_t) slot_of<FM>(k + FN)];
-            e[3 * HT] = spec[(size_t) slot_of<FM>(FN - k)];
-            e[4 * HT] = spec[(size_t) slot_of<FM>((FM - k) & (FM - 1))];
-        }
-    return ct;
+    return std::vector<double2>(); // up 2: phase C runs inside the first inverse pass (build_cd_tab)
 }
 
 std::vector<double2> build_cd_tab(const std::vector<double2>& spec, const std::vector<double2>& tw)

@@ -19,8 +19,9 @@ void build_spectrum(const StageDesc& s, int fft_log2, std::vector<double2>& spec
 
 // [q][r] twiddle tables of the fused kernels: 256 entries W_256^(r q), then 256 entries W_4096^(r q)
 std::vector<double2> build_tw_tab(const std::vector<double2>& tw4096);
-// phase C operands of the v2 fused kernel in thread order (FusedParams::c_tab); up = 1: the layout c1_pair_tab() reads
-std::vector<double2> build_c_tab(const std::vector<double2>& spec_slots4096, const std::vector<double2>& tw4096, int up = 2);
+// phase C operands of the v2 fused kernel's 1x pair in thread order (FusedParams::c_tab, the layout c1_pair_tab() reads);
+// empty for up = 2, whose phase C runs inside the first inverse pass (build_cd_tab)
+std::vector<double2> build_c_tab(const std::vector<double2>& spec_slots4096, const std::vector<double2>& tw4096, int up);
 
 // "2x BlockConvolver -> FracInterpolator" pair: margins and span of the M = 4096 tiles
 struct FusedGeom {

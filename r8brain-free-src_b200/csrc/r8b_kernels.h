@@ -186,10 +186,9 @@ struct FusedParams {
     int up;                  // BlockConvolver up-factor of the fused pair: 2 (default, also when 0) or 1
     int ylen;                // doubles of the tile's stream between the two stages held in shared memory (2*FM for up 2, FM for up 1)
     const double2* cd_tab;   // up == 2, phase C fused into the first inverse pass: [q3 < 16][g < 256] spectrum at slot 16 g + q3,
-                             // then [g < 256] W_M^((g >> 4) + 16 (g & 15)); nullptr: separate phase C from c_tab
-    const double2* c_tab;    // phase C operands in the order the threads consume them: [u < 4][item < 5][ht < 256] --
-                             // item 0 = W_M^k, items 1..4 = spectrum at the slots of k, k+N, N-k, M-k for k = c_freq(ht, u)
-                             // (up == 1: [u < 4][item < 3][ht < 256] -- W_M^k, H[k]/2, H[N-k]/2 -- then 3 entries for k = N/2)
+                             // then [g < 256] W_M^((g >> 4) + 16 (g & 15))
+    const double2* c_tab;    // up == 1: phase C operands in the order the threads consume them: [u < 4][item < 3][ht < 256] --
+                             // W_M^k, H[k]/2, H[N-k]/2 for k = c_freq(ht, u) -- then 3 entries for k = N/2 (v1 kernel: its own table)
 };
 int fused_smem_bytes(int bank_doubles_in_smem);
 int fused_max_span(int lg, int yl, int yr);
