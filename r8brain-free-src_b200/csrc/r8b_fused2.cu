@@ -1,22 +1,27 @@
-// r8b_fused2.cu -- v2 of the fused "2x BlockConvolver -> whole-stepping FracInterpolator" kernel
-// (CDSPResampler.h:218-333; CDSPBlockConvolver.h:252-354 + CDSPFracInterpolator.h:991-1060), the whole
-// process() chain of BASELINE configs 1/2/3 in ONE launch per call.
+// r8b_fused2.cu -- v2 of the fused "BlockConvolver -> FracInterpolator" kernel (CDSPResampler.h:218-333;
+// CDSPBlockConvolver.h:252-354 + CDSPFracInterpolator.h:991-1060): the whole process() chain of BASELINE configs 1/2/3,
+// the tail of the decimating chains (UP = 1), and the lone 2x BlockConvolver of chains that continue with half-band
+// upsamplers (COPY), in ONE launch per call.
 //
-// v1 (r8b_fused.cu) gives an SM to one 512-thread CTA that walks a tile pair through seven block-wide
-// phases; nothing overlaps a barrier, half the CTA idles through the forward transform, and every CTA pays
-// its launch and drain (ncu: fp64 pipe 34 %, warps active 23 %).  v2 is a PERSISTENT CTA per SM made of two
-// independent 256-thread pipelines ("halves").  Each half owns one tile at a time and synchronises only
-// with itself (named barriers, bar.sync id,256); the halves are kept half a period apart by a token
-// (mbarrier ping-pong around the interpolation), so one half's transforms -- latency-bound, few warps --
-// run under the other half's interpolation -- throughput-bound.  Shared tables arrive once per CTA by
-// bulk async copy (cp.async.bulk + mbarrier): the [q][r] twiddle tables and this call's phase-group bank.
-// A tile's 4096 input samples are one contiguous 32 KB run of the caller's block: they are prefetched into
-// L2 a tile ahead (cp.async.bulk.prefetch.L2) and land in the tile buffer's upper half by one bulk copy
-// issued as soon as the half's previous tile has left the buffer; no registers are spent on prefetch.
-// Tiles at the edges of a call (history ring, not yet available input) and misaligned rows are gathered
-// with plain loads.
+// v1 (r8b_fused.cu) gives an SM to one 512-thread CTA that walks a tile pair through seven block-wide phases.  v2 is a
+// PERSISTENT CTA per SM made of two independent 256-thread pipelines ("halves"): each half owns one tile at a time and
+// synchronises only with itself (named barriers, bar.sync id,256), so one half's transforms run under the other half's
+// interpolation.  (An optional mbarrier token that makes the halves take turns at the interpolation -- flags bit 0 --
+// helped the FMA interpolation and hurts the tensor-path one; it is off by default.)  Shared tables arrive once per CTA
+// by bulk async copy (cp.async.bulk + mbarrier): the [q][r] twiddle tables and this call's phase-group bank.  A tile's
+// 4096 input samples are one contiguous 32 KB run of the caller's block or of the previous stage's ring: they are
+// prefetched into L2 a tile ahead (cp.async.bulk.prefetch.L2) and land in the tile buffer's upper half by one bulk copy
+// issued as soon as the half's previous tile has left the buffer; no registers are spent on prefetch.  Tiles at the
+// edges of a call (history ring across a wrap, not yet available input), misaligned rows and typed (int16 .. float32)
+// caller blocks are gathered with plain loads.
 //
-// Shared memory: 2 tile buffers (4096 padded double2 each) + twiddles 8 KB + bank + per-warp store staging.
+// Per tile: real-input forward FFT (2048 complex points), spectrum split x filter spectrum fused into the first inverse
+// pass (UP = 2) or as its own phase (UP = 1), inverse FFT, then the whole-step interpolation as 8x8x4 fp64 matrix
+// products (mma.sync m8n8k4 = DMMA) out of shared memory.  The arithmetic lives in r8b_fused2_core.cuh, which also
+// compiles for the host (tests/cpp/fused2_emul.cpp).
+//
+// Shared memory: 2 tile buffers (4096 + 16 padded double2 each) + twiddles 8 KB + the call's bank (+ per-warp store
+// staging for the FMA interpolation variants only).
 #include "r8b_kernels.h"
 
 #include <cstdint>
