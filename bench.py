@@ -423,12 +423,17 @@ def main():
     e2e = None
     if not args.no_e2e:
         # pinned buffers placed on the GPU's NUMA node (r8bgpu_batch_host_alloc: mmap + mbind + cudaHostRegister)
+        def pinned(cols):
+            try:
+                return torch.from_numpy(batch.host_alloc(cols)), "r8bgpu_batch_host_alloc (NUMA-placed, cudaHostRegister)"
+            except Exception:  # mbind / registration refused on this host: ordinary pinned memory
+                return torch.empty((n_ch, cols), dtype=torch.float64).pin_memory(), "torch pin_memory (fallback)"
         hx = []
         for i in range(2):
-            a = batch.host_alloc(BLOCK)
-            a[:] = synth_block(n_ch, BLOCK, 2000 + i)
-            hx.append(torch.from_numpy(a))
-        hy = torch.from_numpy(batch.host_alloc(cap))
+            t, host_mem = pinned(BLOCK)
+            t.numpy()[:] = synth_block(n_ch, BLOCK, 2000 + i)
+            hx.append(t)
+        hy, host_mem = pinned(cap)
         batch.set_stream(None)
         ke = max(3, min(K, 8))
         for i in range(2):
@@ -448,7 +453,7 @@ def main():
                "h2d_bytes_per_step": n_ch * BLOCK * 8, "d2h_bytes_per_step": int(n_ch * (outs / ke) * 8),
                "steps": ke, "api": "r8bgpu_batch_process_host (pinned host in/out, sync per call)",
                "h2d_gbs_per_gpu": n_ch * BLOCK * 8 * ke / t_e2e / 1e9, "d2h_gbs_per_gpu": n_ch * (outs / ke) * 8 * ke / t_e2e / 1e9,
-               "numa_node": numa_node, "numa_bound": numa_bound}
+               "numa_node": numa_node, "numa_bound": numa_bound, "host_buffers": host_mem}
 
         if world == 1:
             # same call with float32 planar host buffers (r8bgpu_batch_process_host_fmt): what a caller holding

@@ -1,8 +1,8 @@
+# tools/final_run.sh -- reproduces the round-2 numbers quoted in DESIGN.md section 8 / profiles/ on one B200:
+#   GPU tests, smoke, the default bench line (with e2e, CPU baseline, verification), every chain, the ncu summaries.
 set -x
-timeout 500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-for w in cfg2_1024ch_44100_96000_r24 cfg3_1024ch_48000_44100_r24 cfg5_512ch_48000_47999_r24 cfg4_128ch_44100_2822400_r24_extfft cfg3b_1024ch_192000_44100_r24; do
-  extra="--no-cpu"; if [ $w = cfg2_1024ch_44100_96000_r24 ]; then extra=""; fi
-  timeout 200 python bench.py --workload $w $extra 2>/dev/null | tail -1 > gpurun_out/final_$w.json
-  python -c "import json,sys; d=json.load(open(sys.argv[1])); print(sys.argv[1], d['ms_per_step'], d['value'], d['e2e']['value'] if d['e2e'] else None, d['roofline']['frac'], d['roofline']['path']['frac'])" gpurun_out/final_$w.json
-done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 400 python bench.py --steps 20 --warmup 4 2>/dev/null | tail -1 > gpurun_out/final_default.json
+bash tools/r2_all.sh          # every BASELINE chain + the two decimating extras, device-resident, verified
+bash tools/r2_final1.sh       # ncu --set full captures reduced on the box (tools/ncu_report.sh, tools/ncu_summary.py)
