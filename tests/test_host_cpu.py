@@ -193,3 +193,22 @@ def test_whole_stepping_decision_matches_reference(pkg):
         assert (st["order"] == 0) == ok, (src, dst, ok, st)
         if ok:
             assert (st["in_step"], st["out_step"]) == (a, b), (src, dst, a, b, st)
+
+
+def test_multi_device_host_plumbing(tmp_path):
+    """csrc/r8b_multi.cpp on the CPU: shard worker pool (results by shard, error relay from the worker's own thread,
+    20000 back-to-back rounds), NUMA thread placement inside the process mask, pinned allocator refusing without a device."""
+    import shutil
+    import subprocess
+    cuda = next((d for d in (os.environ.get("CUDA_HOME"), "/usr/local/cuda")
+                 if d and os.path.exists(os.path.join(d, "include", "cuda_runtime.h"))), None)
+    if cuda is None or shutil.which("g++") is None:
+        pytest.skip("CUDA headers / g++ not found")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "multi_host")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(cuda, "include"), "-o", exe,
+                    os.path.join(root, "tests", "cpp", "multi_host.cpp"),
+                    os.path.join(root, "r8brain-free-src_b200", "csrc", "r8b_multi.cpp"),
+                    "-L" + os.path.join(cuda, "lib64"), "-lcudart_static", "-ldl", "-lrt"], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "FAIL" not in r.stdout and "OK" in r.stdout, r.stdout
