@@ -212,3 +212,36 @@ def test_multi_device_host_plumbing(tmp_path):
                     "-L" + os.path.join(cuda, "lib64"), "-lcudart_static", "-ldl", "-lrt"], check=True)
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0 and "FAIL" not in r.stdout and "OK" in r.stdout, r.stdout
+
+
+@pytest.mark.skipif(not (ou.have_ref('e0') and ou.have_ref('e1')), reason='compiled reference not present')
+def test_scheduler_random_sweep_matches_reference(pkg):
+    """Seeded sweep over rate pairs x presets x transition bands x R8B_EXTFFT with ragged call lengths: per-call output
+    counts, getMaxOutLen, getInLenBeforeOutPos and getInputRequiredForOutput are the reference's integers
+    (CDSPResampler.h:117-214, 559-575) on every planner branch the sweep reaches."""
+    rng = np.random.default_rng(20260923)
+    rates = [8000.0, 11025.0, 16000.0, 22050.0, 32000.0, 44100.0, 48000.0, 88200.0, 96000.0, 176400.0, 192000.0,
+             352800.0, 384000.0, 2822400.0, 47999.0, 44100.5, 12345.0, 96001.0]
+    attens = [pkg.ATTEN_16, pkg.ATTEN_16IR, pkg.ATTEN_24, 206.91, 60.0]
+    tbs = [0.5, 2.0, 3.0, 7.0, 20.0, 45.0]
+    refs = {0: ou.RefOracle("e0"), 1: ou.RefOracle("e1")}
+    kinds = set()
+    n_done = 0
+    for _ in range(400):
+        src, dst = (float(v) for v in rng.choice(rates, 2, replace=False))
+        att, tb, ext = float(rng.choice(attens)), float(rng.choice(tbs)), int(rng.integers(0, 2))
+        max_len = int(rng.choice([64, 1000, 4096]))
+        lens = [max_len] * 3 + [int(v) for v in rng.integers(0, max_len + 1, 8)] + [0, 1, max_len]
+        plan = pkg.Plan(src, dst, max_len, tb, att, extfft=ext)
+        r = refs[ext].Resampler(src, dst, max_len, tb, att)
+        x = np.zeros(max_len)
+        what = (src, dst, att, tb, ext, max_len)
+        assert plan.simulate(lens) == [len(r.process(x[:l])) for l in lens], what
+        assert plan.max_out_len == r.max_out_len, what
+        for pos in (0, 17, 1000):
+            assert plan.in_len_before_out_pos(pos) == r.in_len_before_out_pos(pos), what
+        for n in (1, 999):
+            assert plan.input_required_for_output(n) == r.input_required_for_output(n), what
+        kinds.update(s["kind"] for s in plan.stages())
+        n_done += 1
+    assert n_done == 400 and len(kinds) >= 5, kinds  # BlockConv, both interpolators, both half-band stages were reached
