@@ -245,3 +245,38 @@ def test_scheduler_random_sweep_matches_reference(pkg):
         kinds.update(s["kind"] for s in plan.stages())
         n_done += 1
     assert n_done == 400 and len(kinds) >= 5, kinds  # BlockConv, both interpolators, both half-band stages were reached
+
+
+def test_filter_design_random_sweep_matches_reference(pkg, ref):
+    """Seeded sweep of the host filter design against the reference's (CDSPFIRFilter.h:220-537,
+    CDSPFracInterpolator.h:61-189): low-pass kernel length, block size and spectrum over random cut-offs, transition
+    bands, attenuations and gains; fractional-delay banks bit for bit over random whole-stepping / order-2 ratios."""
+    rng = np.random.default_rng(77)
+    for _ in range(60):
+        nf = float(rng.choice([0.5, 1 / 3, 0.25, 0.125, float(rng.uniform(0.05, 0.5))]))
+        tb = float(rng.choice([0.5, 1.0, 2.0, 3.0, 7.5, 20.0, 45.0, float(rng.uniform(0.5, 45.0))]))
+        att = float(rng.choice([49.0, 60.0, 109.56, 136.45, 180.15, 206.91, 218.0, float(rng.uniform(49.0, 218.0))]))
+        gain = float(rng.choice([1.0, 2.0, 3.0, 0.5, 0.03125]))
+        p = pkg.Plan.single_stage(0, [nf, tb, att, gain, 1, 1], 1024)
+        st = p.stages()[0]
+        r = ref.lpfilter(nf, tb, att, gain)
+        what = (nf, tb, att, gain)
+        assert st["kernel_len"] == r["kernel_len"] and st["block_len_bits"] == r["block_len_bits"], what
+        h = p.stage_data(0)
+        L = (st["kernel_len"] - 1) // 2
+        b2 = 2 << r["block_len_bits"]
+        z = np.zeros(b2)
+        z[:L + 1] = h[L:]
+        z[b2 - L:] = h[:L]
+        assert np.max(np.abs(np.fft.rfft(z).real - r["spectrum"])) <= 8 * ou.EPS * gain, what
+        # DC gain (what the chain's level rests on): the exact tap sum is the reference's DC bin
+        import math
+        assert abs(math.fsum(h) - r["spectrum"][0]) <= 8 * ou.EPS * gain, what
+    rates = [44100.0, 48000.0, 88200.0, 96000.0, 47999.0, 32000.0, 12345.0, 96001.0, 176400.0, 22050.5]
+    for _ in range(30):
+        src, dst = (float(v) for v in rng.choice(rates, 2, replace=False))
+        att, third = float(rng.choice([109.56, 136.45, 180.15, 206.91])), int(rng.integers(0, 2))
+        ok, a, b = ref.whole_stepping(src, dst)
+        r = ref.fracbank(b if ok else -1, 1 if ok else 3, 2 if ok else 8, att, bool(third))
+        p = pkg.Plan.single_stage(1, [src, dst, att, third], 1024)
+        assert np.array_equal(p.stage_data(0).reshape(r["table"].shape), r["table"]), (src, dst, att, third)
