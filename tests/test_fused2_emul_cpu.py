@@ -104,3 +104,26 @@ def test_downsampling_chain_padded_y_layout(emul):
 def test_full_block_and_presets(emul):
     _run(emul, 44100.0, 96000.0, 65536, [65536, 65536])
     _run(emul, 44100.0, 48000.0, 4096, [4096] * 4, atten=136.45)
+
+
+def test_seeded_sweep_of_rate_pairs_and_ragged_calls(emul):
+    """Every rate pair here plans to BlockConvolver (2x or 1x) -> whole-stepping interpolator; presets, transition
+    bands, call lengths and the interpolation formulation (register-tiled FMA / tensor-path fragments) are drawn."""
+    rng = np.random.default_rng(4242)
+    pairs = [(44100.0, 96000.0), (48000.0, 44100.0), (44100.0, 48000.0), (32000.0, 44100.0), (48000.0, 88200.0),
+             (96000.0, 44100.0), (88200.0, 48000.0), (44100.0, 64000.0), (100000.0, 44100.0), (22050.0, 32000.0)]
+    done = 0
+    for src, dst in pairs:
+        for _ in range(2):
+            att = float(rng.choice([136.45, 180.15, 206.91]))
+            tb = float(rng.choice([2.0, 3.0, 6.0]))
+            max_len = int(rng.choice([2048, 4096, 8192]))
+            lens = [max_len, max_len] + [int(v) for v in rng.integers(0, max_len + 1, 4)] + [max_len]
+            glog = int(rng.choice([-1, 8]))
+            h = emul.f2emul_create(src, dst, max_len, tb, att, glog)
+            if not h:   # this preset does not take the fused chain for the pair (kernel too long for the tile)
+                continue
+            emul.f2emul_destroy(h)
+            _run(emul, src, dst, max_len, lens, glog=glog, atten=att, tb=tb, seed=int(rng.integers(1 << 30)))
+            done += 1
+    assert done >= 12, done
